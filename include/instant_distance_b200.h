@@ -1,0 +1,140 @@
+/*
+ * instant_distance_b200.h — C ABI of the B200-native HNSW build-and-search engine.
+ *
+ * This is the drop-in boundary for djc/instant-distance's f32-vector hot path.  Every entry point below
+ * names the reference interface it replaces (file:line under the reference tree; core =
+ * instant-distance/src/lib.rs, types = instant-distance/src/types.rs, py = instant-distance-py/src/lib.rs).
+ * A Rust `-sys` binding, the PyO3 module, or any other FFI binds exactly these symbols.
+ *
+ * Conventions
+ *   - Plain C types only; all index state lives in GPU HBM behind an opaque handle.
+ *   - Host-buffer calls copy in/out; the caller keeps ownership of every buffer it passes.
+ *   - Every function returns an idb_status; idb_last_error() gives the thread-local message.
+ *   - There is NO CPU fallback: without a CUDA device every compute call returns IDB_ERR_CUDA.
+ *   - Points are f32 vectors under squared-L2 (the reference's FloatArray metric, py:378-421), any dim >= 1,
+ *     computed in one canonical fp32 summation order so results are bit-reproducible.
+ *   - PointIds are u32; IDB_INVALID (u32::MAX) is the reference's INVALID sentinel (types:293).
+ */
+#ifndef INSTANT_DISTANCE_B200_H
+#define INSTANT_DISTANCE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDB_INVALID 0xFFFFFFFFu
+
+#if defined(__GNUC__)
+#define IDB_API __attribute__((visibility("default")))
+#else
+#define IDB_API
+#endif
+
+typedef enum idb_status {
+    IDB_OK = 0,
+    IDB_ERR_INVALID_ARG = 1,   /* null pointer, dim == 0, N >= u32::MAX (core:256), unsupported M / ef ... */
+    IDB_ERR_OOM = 2,           /* host or device allocation failed */
+    IDB_ERR_CUDA = 3,          /* no device / CUDA runtime error (message has the CUDA error string) */
+    IDB_ERR_NCCL = 4,
+    IDB_ERR_IO = 5,
+    IDB_ERR_FORMAT = 6,        /* malformed index file */
+    IDB_ERR_CAPACITY = 7,      /* an internal per-query structure overflowed even after the retry pass */
+    IDB_ERR_UNSUPPORTED = 8
+} idb_status;
+
+/* Opaque index handle: replaces `Hnsw<P>` (core:193-199) for P = f32 vector. */
+typedef struct idb_index idb_index;
+
+/* Builder (core:23-31) + Heuristic (core:115-119).  M is a compile-time const 32 in the reference
+ * (core:787); it is a run-time field here because BASELINE.json's configs name M = 16 and M = 24. */
+typedef struct idb_params {
+    uint32_t M;                 /* reference: const M = 32 (core:787); supported 2..64 */
+    uint32_t ef_construction;   /* Builder::ef_construction (core:35-38), default 100 (core:105) */
+    uint32_t ef_search;         /* Builder::ef_search       (core:44-47), default 100 (core:104) */
+    float    ml;                /* Builder::ml              (core:57-60), default 1/ln(M) (core:107) */
+    uint64_t seed;              /* Builder::seed            (core:65-68) */
+    int32_t  heuristic;         /* Builder::select_heuristic(Some/None) (core:49-52); default Some */
+    int32_t  extend_candidates; /* Heuristic::extend_candidates (core:117), default false */
+    int32_t  keep_pruned;       /* Heuristic::keep_pruned       (core:118), default true  */
+    uint32_t insert_batch;      /* GPU build: concurrent inserts per step (rayon's worker count in the
+                                   reference, core:316-318).  0 = auto, 1 = strictly sequential order. */
+    int32_t  device;            /* CUDA device ordinal */
+} idb_params;
+
+/* Builder::default() (core:101-113) — except `seed`, which the reference draws from entropy; here 0. */
+IDB_API idb_status idb_params_default(idb_params* p);
+
+/* Builder::build_hnsw(points) -> (Hnsw, Vec<PointId>) (core:83-85 -> Hnsw::new core:209-345).
+ * rows: n x dim row-major host f32.  out_ids[i] = PointId assigned to input row i (core:262-270); may be NULL. */
+IDB_API idb_status idb_build_f32(const float* rows, uint64_t n, uint32_t dim, const idb_params* params,
+                         idb_index** out_index, uint32_t* out_ids);
+
+/* "Search a given graph": adopt a graph built elsewhere (the reference, the oracle, a loaded .idx file).
+ * This is the parity entry point.  Mirrors the fields of `Hnsw` (core:194-199):
+ *   points   n x dim, PointId order                       (Hnsw::points)
+ *   zero     n x 2M u32, INVALID-terminated rows          (Hnsw::zero, ZeroNode types:83-85)
+ *   upper[l] upper_n[l] x M u32 for layer l+1             (Hnsw::layers, UpperNode types:63) */
+IDB_API idb_status idb_index_from_graph_f32(const float* points, uint64_t n, uint32_t dim, uint32_t M, uint32_t ef_search,
+                                    const uint32_t* zero, uint32_t n_upper, const uint32_t* const* upper,
+                                    const uint64_t* upper_n, int32_t device, idb_index** out_index);
+
+/* Hnsw::search(point, &mut Search) (core:352-383), batched: one independent search per query row.
+ * The reference returns the whole `nearest` list (<= ef_search items, ascending by (distance, pid));
+ * callers take the first k.  Here: out_ids/out_dist are nq x k (row q holds the first min(len,k) items,
+ * padded with IDB_INVALID / +inf), out_len[q] = len(nearest) (what `ExactSizeIterator::len` reports).
+ * ef_search == 0 uses the index's own ef_search (Hnsw::ef_search, core:195).  out_dist / out_len may be NULL. */
+IDB_API idb_status idb_search_batch_f32(idb_index* index, const float* queries, uint64_t nq, uint32_t ef_search, uint32_t k,
+                                uint32_t* out_ids, float* out_dist, uint32_t* out_len);
+
+/* Same, with queries and outputs already resident in HBM (device pointers, same device as the index;
+ * d_queries is nq x dim row-major).  Enqueues on idb_index_stream(index) and returns without syncing. */
+IDB_API idb_status idb_search_batch_device(idb_index* index, const float* d_queries, uint64_t nq, uint32_t ef_search, uint32_t k,
+                                   uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len);
+
+/* Per-query traversal counters of the LAST search call on this index (for the roofline accounting,
+ * SURVEY §8d): out is nq x 4 u64 = {n_expand_upper, n_dist_upper, n_expand_zero, n_dist_zero}. */
+IDB_API idb_status idb_last_search_counters(idb_index* index, uint64_t nq, uint64_t* out);
+
+/* Introspection: Hnsw::iter / Index<PointId> (core:386-391, types:269-275) and the graph itself. */
+typedef struct idb_info {
+    uint64_t n;
+    uint32_t dim;
+    uint32_t M;
+    uint32_t ef_search;
+    uint32_t n_layers;          /* 0 for an empty index, else 1 + number of upper layers */
+    uint64_t layer_n[32];       /* node count per layer, [0] = n */
+    int32_t  device;
+} idb_info;
+IDB_API idb_status idb_index_info(const idb_index* index, idb_info* out);
+IDB_API idb_status idb_index_export_points(const idb_index* index, float* out /* n x dim */);
+IDB_API idb_status idb_index_export_zero(const idb_index* index, uint32_t* out /* n x 2M */);
+IDB_API idb_status idb_index_export_upper(const idb_index* index, uint32_t layer /* 1-based */, uint32_t* out /* n_l x M */);
+
+/* Measurement hooks (bench.py): when enabled, CUDA events are recorded on the index stream immediately around the
+ * dominant kernel of each call (K1 search_layer for searches); idb_index_last_kernel_ms waits for that kernel and
+ * returns its duration and how many of this library's kernels the last call launched. */
+IDB_API idb_status idb_index_set_profiling(idb_index* index, int32_t enabled);
+IDB_API idb_status idb_index_last_kernel_ms(idb_index* index, float* out_ms, uint32_t* out_launches);
+
+IDB_API void* idb_index_stream(idb_index* index);      /* the cudaStream_t all work of this index is enqueued on */
+IDB_API idb_status idb_index_sync(idb_index* index);   /* cudaStreamSynchronize on it */
+IDB_API void idb_index_free(idb_index* index);         /* Drop for Hnsw */
+
+/* The canonical squared-L2 of one pair, evaluated on the device (used by parity tests; FloatArray::distance, py:378-421). */
+IDB_API idb_status idb_distance_f32(const float* a, const float* b, uint32_t dim, int32_t device, float* out);
+
+/* Pinned host memory helpers for callers that want true async H2D/D2H. */
+IDB_API idb_status idb_host_alloc(size_t bytes, void** out);
+IDB_API void idb_host_free(void* p);
+
+IDB_API const char* idb_last_error(void);
+IDB_API const char* idb_version(void);
+IDB_API int32_t idb_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INSTANT_DISTANCE_B200_H */

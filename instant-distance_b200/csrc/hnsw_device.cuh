@@ -1,0 +1,570 @@
+// hnsw_device.cuh — warp-level HNSW traversal for sm_100a (one warp per live query / insert).
+//
+// Restates, as a warp-synchronous data-parallel program, the reference's
+//   Search::search  (search_layer, Alg. 2)   instant-distance/src/lib.rs:598-614
+//   Search::push                              lib.rs:704-720
+//   Search::cull / reset                      lib.rs:729-755
+//   Hnsw::search driver                       lib.rs:352-383   (and Construction::insert's descent, lib.rs:443-463)
+//   Visited                                   types.rs:13-59
+//   NearestIter + take(links)                 types.rs:172-192, lib.rs:606
+//   Candidate ordering                        types.rs:228-234
+// The traversal is BIT-IDENTICAL to the sequential reference (same expansions, same distance evaluations,
+// same result list), see DESIGN.md "exactness under parallel execution":
+//   * `nearest` is a sorted array of u64 keys  (canonical distance bits << 32 | pid)  in shared memory;
+//     bit 63 (the sign bit of the non-negative distance) flags "already expanded".
+//   * `candidates` is never materialised: it equals {unexpanded entries of nearest} U {tie list}, where the
+//     tie list holds evicted, unexpanded, ADMITTED candidates whose distance equals the current furthest
+//     distance (the reference's stop test is strict `>` and distance-only, lib.rs:601).
+//   * a whole row (<= 2M ids) is processed at once: visited test-and-set per lane, distances 32 at a time,
+//     admission resolved by the row-order rank rule  rank_S(x) + #{earlier admitted < x} < ef  (lib.rs:712-714).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace idb {
+
+constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+constexpr uint64_t kFlagExpanded = 1ull << 63;
+constexpr uint64_t kKeyMask = ~kFlagExpanded;
+constexpr uint64_t kKeyNone = ~0ull;          // sorts after every real key (real dist bits <= 0x7fc00000)
+constexpr int kSmallVisSlots = 512;           // shared-memory visited set used on the ef=1 layers
+constexpr int kTieCap = 1024;                 // per-warp tie list capacity (global memory)
+constexpr uint32_t kFullMask = 0xFFFFFFFFu;
+
+enum QueryStatus : uint32_t { kQueryOk = 0, kQueryVisitedOverflow = 1, kQueryTieOverflow = 2 };
+
+struct GraphView {
+    const float4* points;        // n x nchunks float4 (row stride = dim rounded up to 4 floats, zero padded)
+    uint32_t nchunks;            // float4 chunks per row
+    const uint32_t* zero;        // n x 2M
+    const uint32_t* const* upper;  // device array: upper[l-1] = n_l x M
+    uint32_t n_upper;
+    uint32_t M;
+    uint64_t n;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Canonical squared-L2 (DESIGN.md "canonical distance"; the CPU checker restates the same order):
+//   lane l owns float4 chunks l, l+32, l+64, ...; four fmaf chains (one per float4 component);
+//   lane sum (a0+a1)+(a2+a3); xor butterfly over lanes with offsets 16, 8, 4, 2, 1.
+// ---------------------------------------------------------------------------------------------------------
+template <int CH>
+__device__ __forceinline__ float lane_partial(const float4 (&q)[CH], const float4 (&v)[CH]) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        float d0 = __fsub_rn(q[j].x, v[j].x), d1 = __fsub_rn(q[j].y, v[j].y);
+        float d2 = __fsub_rn(q[j].z, v[j].z), d3 = __fsub_rn(q[j].w, v[j].w);
+        a0 = __fmaf_rn(d0, d0, a0);
+        a1 = __fmaf_rn(d1, d1, a1);
+        a2 = __fmaf_rn(d2, d2, a2);
+        a3 = __fmaf_rn(d3, d3, a3);
+    }
+    return __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+}
+
+// Butterfly for ONE vector: every lane ends with the total.
+__device__ __forceinline__ float butterfly_sum(float s) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s = __fadd_rn(s, __shfl_xor_sync(kFullMask, s, off));
+    return s;
+}
+
+// Butterfly for 32 vectors at once ("transposing" reduction, 31 shuffles instead of 160): p[i] is this lane's
+// partial for vector i; on return lane l holds the total of vector l.  Same add tree as butterfly_sum.
+__device__ __forceinline__ float transpose_reduce32(float (&p)[32], int lane) {
+#define IDB_TR_STAGE(OFF)                                                        \
+    {                                                                            \
+        const bool up = (lane & OFF) != 0;                                       \
+        _Pragma("unroll") for (int i = 0; i < OFF; ++i) {                        \
+            float send = up ? p[i] : p[i + OFF];                                 \
+            float keep = up ? p[i + OFF] : p[i];                                 \
+            p[i] = __fadd_rn(keep, __shfl_xor_sync(kFullMask, send, OFF));       \
+        }                                                                        \
+    }
+    IDB_TR_STAGE(16) IDB_TR_STAGE(8) IDB_TR_STAGE(4) IDB_TR_STAGE(2) IDB_TR_STAGE(1)
+#undef IDB_TR_STAGE
+    return p[0];
+}
+
+__device__ __forceinline__ uint32_t canon_bits(float d) {
+    uint32_t b = __float_as_uint(d);
+    if ((b & 0x7fffffffu) > 0x7f800000u) b = 0x7fc00000u;  // NaN: greatest, equal to itself (ordered-float)
+    if (b == 0x80000000u) b = 0u;
+    return b;
+}
+__device__ __forceinline__ uint64_t mk_key(float d, uint32_t pid) { return ((uint64_t)canon_bits(d) << 32) | pid; }
+__device__ __forceinline__ uint32_t key_pid(uint64_t k) { return (uint32_t)k; }
+__device__ __forceinline__ uint32_t key_dbits(uint64_t k) { return (uint32_t)((k & kKeyMask) >> 32); }
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(kFullMask, (uint32_t)v, src), hi = __shfl_sync(kFullMask, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Visited (types.rs:13-59): exact set of PointIds.  Two tiers, both open addressing with linear probing:
+//   small: kSmallVisSlots u32 in shared memory (the ef=1 layers touch ~30 ids per layer);
+//   big:   `gslots` u32 in global memory, private to this warp, L2 resident (layer 0 / ef_construction).
+// `clear()` (lib.rs:735, 750) wipes whichever tier is live.  Empty slot = kInvalid (never a valid PointId).
+// ---------------------------------------------------------------------------------------------------------
+struct VisitedSet {
+    uint32_t* small;   // shared
+    uint32_t* big;     // global
+    uint32_t gslots;   // power of two
+    uint32_t gshift;   // 32 - log2(gslots)
+    uint32_t count;
+    bool use_big;
+};
+
+__device__ __forceinline__ uint32_t vis_hash(uint32_t pid) { return pid * 0x9E3779B1u; }
+
+__device__ __forceinline__ bool vis_insert_small(uint32_t* tab, uint32_t pid) {
+    uint32_t h = vis_hash(pid) >> (32 - 9);
+    static_assert(kSmallVisSlots == 512, "shift above assumes 512 slots");
+    for (;;) {
+        uint32_t old = atomicCAS(&tab[h], kInvalid, pid);
+        if (old == kInvalid) return true;
+        if (old == pid) return false;
+        h = (h + 1) & (kSmallVisSlots - 1);
+    }
+}
+__device__ __forceinline__ bool vis_insert_big(uint32_t* tab, uint32_t gshift, uint32_t gmask, uint32_t pid) {
+    uint32_t h = vis_hash(pid) >> gshift;
+    for (;;) {
+        uint32_t old = atomicCAS(&tab[h], kInvalid, pid);
+        if (old == kInvalid) return true;
+        if (old == pid) return false;
+        h = (h + 1) & gmask;
+    }
+}
+
+__device__ __forceinline__ void vis_clear_small(VisitedSet& v, int lane) {
+#pragma unroll
+    for (int i = 0; i < kSmallVisSlots / 32; ++i) v.small[lane + 32 * i] = kInvalid;
+    __syncwarp();
+}
+__device__ __forceinline__ void vis_clear_big(VisitedSet& v, int lane) {
+    uint4* p = reinterpret_cast<uint4*>(v.big);
+    const uint4 e = make_uint4(kInvalid, kInvalid, kInvalid, kInvalid);
+    for (uint32_t i = lane; i < v.gslots / 4; i += 32) __stcg(p + i, e);
+    __threadfence();  // plain stores must be ordered before later atomics from other lanes
+    __syncwarp();
+}
+// Visited::clear (types.rs:48-58); `next_big` selects the tier for the layer about to be searched.
+__device__ __forceinline__ void vis_clear(VisitedSet& v, int lane, bool next_big) {
+    if (v.use_big) vis_clear_big(v, lane); else vis_clear_small(v, lane);
+    v.count = 0;
+    v.use_big = next_big;
+}
+__device__ __forceinline__ void vis_migrate_to_big(VisitedSet& v, int lane) {
+#pragma unroll 4
+    for (int i = 0; i < kSmallVisSlots / 32; ++i) {
+        uint32_t x = v.small[lane + 32 * i];
+        if (x != kInvalid) vis_insert_big(v.big, v.gshift, v.gslots - 1, x);
+    }
+    __syncwarp();
+    vis_clear_small(v, lane);
+    v.use_big = true;
+}
+// Visited::insert (types.rs:32-40) for one id per lane.  Returns false for lanes with !want.
+// Caller guarantees capacity via vis_reserve.
+__device__ __forceinline__ bool vis_insert(VisitedSet& v, uint32_t pid, bool want) {
+    bool fresh = false;
+    if (want) fresh = v.use_big ? vis_insert_big(v.big, v.gshift, v.gslots - 1, pid) : vis_insert_small(v.small, pid);
+    return fresh;
+}
+// Make room for `incoming` more ids.  Returns false if the big table would exceed 3/4 load (query is aborted
+// with kQueryVisitedOverflow and retried by the host with a larger table).
+__device__ __forceinline__ bool vis_reserve(VisitedSet& v, uint32_t incoming, int lane) {
+    if (!v.use_big && v.count + incoming > kSmallVisSlots / 2) vis_migrate_to_big(v, lane);
+    if (v.use_big && v.count + incoming > (v.gslots / 4) * 3) return false;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-warp traversal state.
+// ---------------------------------------------------------------------------------------------------------
+struct WarpState {
+    uint64_t* near_base;     // shared: two buffers of near_len keys each (ping-pong for the merge)
+    uint32_t near_len;       // 32*EF_T
+    uint32_t* cpid;          // shared: 128 compacted new ids of the current row
+    uint64_t* ties;          // global: kTieCap keys
+    int cur;                 // live near buffer
+    uint32_t cnt;            // len(nearest)
+    uint32_t ntie;
+    uint32_t status;
+    uint32_t n_expand, n_dist;   // per-layer instrumentation (SURVEY §8d counters)
+    VisitedSet vis;
+};
+
+__device__ __forceinline__ uint32_t lower_bound_keys(const uint64_t* a, uint32_t n, uint64_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if ((a[mid] & kKeyMask) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Distances from q to the (<= 32) points whose ids sit one per lane in `mypid` (lanes >= gcount: ignored).
+// Lane l returns the canonical squared-L2 to point mypid@lane l.
+template <int CH, int B>
+__device__ __forceinline__ float group_distance(const GraphView& g, const float4 (&q)[CH], uint32_t mypid, uint32_t gcount,
+                                                int lane) {
+    float p[32];
+#pragma unroll
+    for (int b = 0; b < 32; b += B) {
+        if ((uint32_t)b < gcount) {  // warp-uniform
+            float4 v[B][CH];
+#pragma unroll
+            for (int i = 0; i < B; ++i) {
+                uint32_t pid = __shfl_sync(kFullMask, mypid, b + i);
+                const bool ok = (uint32_t)(b + i) < gcount;
+                const float4* row = g.points + (size_t)pid * g.nchunks;
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const uint32_t c = lane + 32 * j;
+                    v[i][j] = (ok && c < g.nchunks) ? __ldg(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < B; ++i) p[b + i] = lane_partial<CH>(q, v[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < B; ++i) p[b + i] = 0.f;
+        }
+    }
+    return transpose_reduce32(p, lane);
+}
+
+// Rare path: something was evicted while its distance equals the new furthest distance.  Such an entry stays a
+// live candidate in the reference (strict `>` at lib.rs:601) iff it is unexpanded and had been ADMITTED
+// (pushed on `candidates`, lib.rs:719).  Admission of row entry j: rank_S(j) + #{i<j in row order, i in A, key_i < key_j} < ef.
+template <int ROW_T, int EF_T>
+__device__ __forceinline__ void collect_ties(WarpState& s, const uint64_t* old_near, uint32_t old_cnt, const uint32_t (&shift)[EF_T],
+                                          const uint64_t (&keyg)[ROW_T], const uint32_t (&rank)[ROW_T], const bool (&inA)[ROW_T],
+                                          const uint32_t (&less)[ROW_T], uint32_t ef_cur, uint32_t fbits, int lane) {
+    // (a) evicted members of S
+#pragma unroll
+    for (int t = 0; t < EF_T; ++t) {
+        uint32_t idx = lane + 32 * t;
+        bool tie = false;
+        uint64_t k = 0;
+        if (idx < old_cnt) {
+            k = old_near[idx];
+            tie = (idx + shift[t] >= ef_cur) && !(k & kFlagExpanded) && key_dbits(k) == fbits;
+        }
+        uint32_t m = __ballot_sync(kFullMask, tie);
+        if (m) {
+            uint32_t pos = s.ntie + __popc(m & ((1u << lane) - 1));
+            if (tie && pos < kTieCap) s.ties[pos] = k;
+            s.ntie += __popc(m);
+        }
+    }
+    // (b) evicted members of A that were admitted in row order
+#pragma unroll
+    for (int g = 0; g < ROW_T; ++g) {
+        bool cand = inA[g] && (rank[g] + less[g] >= ef_cur) && key_dbits(keyg[g]) == fbits;
+        uint32_t earlier = 0;
+        // count A entries earlier in row order (compacted index c' = 32*g2 + lane' < c = 32*g + lane) with smaller key
+#pragma unroll
+        for (int g2 = 0; g2 < ROW_T; ++g2) {
+            uint32_t mA = __ballot_sync(kFullMask, inA[g2]);
+            while (mA) {
+                int src = __ffs(mA) - 1;
+                mA &= mA - 1;
+                uint64_t ak = shfl64(keyg[g2], src);
+                if ((32 * g2 + src) < (32 * g + lane) && ak < keyg[g]) earlier++;
+            }
+        }
+        bool tie = cand && (rank[g] + earlier < ef_cur);
+        uint32_t m = __ballot_sync(kFullMask, tie);
+        if (m) {
+            uint32_t pos = s.ntie + __popc(m & ((1u << lane) - 1));
+            if (tie && pos < kTieCap) s.ties[pos] = keyg[g];
+            s.ntie += __popc(m);
+        }
+    }
+    if (s.ntie > kTieCap) { s.status = kQueryTieOverflow; s.ntie = kTieCap; }
+    __threadfence_block();
+    __syncwarp();
+}
+
+// Pop the smallest key of the tie list (BinaryHeap::pop order among ties).
+__device__ __forceinline__ uint64_t pop_min_tie(WarpState& s, int lane) {
+    uint64_t best = kKeyNone;
+    uint32_t bi = 0;
+    for (uint32_t i = lane; i < s.ntie; i += 32) {
+        uint64_t k = s.ties[i];
+        if (k < best) { best = k; bi = i; }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        uint64_t ok = shfl64(best, lane ^ off);
+        uint32_t oi = __shfl_xor_sync(kFullMask, bi, off);
+        if (ok < best) { best = ok; bi = oi; }
+    }
+    if (lane == 0) s.ties[bi] = s.ties[s.ntie - 1];
+    s.ntie--;
+    __threadfence_block();
+    __syncwarp();
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// search_layer (lib.rs:598-614) over one layer.
+//   rows/width : adjacency table of this layer (fixed stride `width` u32 per node)
+//   links      : `.take(links)` (lib.rs:606)
+//   ef_cur     : Search::ef for this layer
+// Pre: near[0..cnt) sorted, unexpanded entries are the enter points (candidates), visited holds them.
+// kLive: rows may be rewritten concurrently (GPU build) -> read them through L2 (ld.global.cg), not the
+// read-only/L1 path.
+// ---------------------------------------------------------------------------------------------------------
+template <int CH, int ROW_T, int EF_T, int B, bool kLive>
+__device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, const float4 (&q)[CH], const uint32_t* rows,
+                                             uint32_t width, uint32_t links, uint32_t ef_cur, int lane) {
+    const uint32_t lt_mask = (1u << lane) - 1;
+    for (;;) {
+        uint64_t* near = (s.near_base + s.cur * s.near_len);
+        // ---- pop the min candidate: first unexpanded entry of nearest, else the smallest tie ----------
+        int sel = -1;
+#pragma unroll
+        for (int t = 0; t < EF_T; ++t) {
+            if (sel < 0) {
+                uint32_t idx = lane + 32 * t;
+                bool un = idx < s.cnt && !(near[idx] & kFlagExpanded);
+                uint32_t m = __ballot_sync(kFullMask, un);
+                if (m) sel = 32 * t + __ffs(m) - 1;
+            }
+        }
+        uint32_t cpid;
+        if (sel >= 0) {
+            uint64_t ck = near[sel];
+            cpid = key_pid(ck);
+            __syncwarp();
+            if (lane == 0) near[sel] = ck | kFlagExpanded;
+            __syncwarp();
+        } else if (s.ntie > 0) {
+            cpid = key_pid(pop_min_tie(s, lane));  // dist == furthest dist by invariant -> not `>` -> expanded
+        } else {
+            break;  // heap empty, or its min is strictly beyond the furthest result (lib.rs:601-603)
+        }
+        s.n_expand++;
+
+        // ---- row of the candidate: NearestIter stops at the first INVALID (types.rs:178-191) ----------
+        uint32_t ent[ROW_T];
+        const uint32_t* row = rows + (size_t)cpid * width;
+#pragma unroll
+        for (int t = 0; t < ROW_T; ++t) {
+            uint32_t e = lane + 32 * t;
+            ent[t] = kInvalid;
+            if (e < links) ent[t] = kLive ? __ldcg(row + e) : __ldg(row + e);
+        }
+        uint32_t count = 32 * ROW_T;
+#pragma unroll
+        for (int t = ROW_T - 1; t >= 0; --t) {
+            uint32_t m = __ballot_sync(kFullMask, ent[t] == kInvalid);
+            if (m) count = 32 * t + __ffs(m) - 1;
+        }
+        if (count == 0) continue;
+
+        // ---- visited.insert for every row entry (lib.rs:705) -------------------------------------------
+        if (!vis_reserve(s.vis, count, lane)) { s.status = kQueryVisitedOverflow; break; }
+        bool isnew[ROW_T];
+        uint32_t cpos[ROW_T];
+        uint32_t n_new = 0;
+#pragma unroll
+        for (int t = 0; t < ROW_T; ++t) {
+            isnew[t] = vis_insert(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count);
+            uint32_t m = __ballot_sync(kFullMask, isnew[t]);
+            cpos[t] = n_new + __popc(m & lt_mask);
+            n_new += __popc(m);
+        }
+        s.vis.count += n_new;
+        s.n_dist += n_new;
+        if (n_new == 0) continue;
+
+        // ---- compact the new ids in row order, one per lane per group of 32 ----------------------------
+#pragma unroll
+        for (int t = 0; t < ROW_T; ++t)
+            if (isnew[t]) s.cpid[cpos[t]] = ent[t];
+        __syncwarp();
+        uint32_t mypid[ROW_T];
+        uint64_t keyg[ROW_T];
+#pragma unroll
+        for (int gi = 0; gi < ROW_T; ++gi) {
+            uint32_t c = 32 * gi + lane;
+            mypid[gi] = c < n_new ? s.cpid[c] : 0u;
+            keyg[gi] = kKeyNone;
+        }
+        __syncwarp();
+
+        // ---- distances (lib.rs:709-710), 32 rows per group ---------------------------------------------
+#pragma unroll
+        for (int gi = 0; gi < ROW_T; ++gi) {
+            if ((uint32_t)(32 * gi) < n_new) {
+                uint32_t gcount = min(32u, n_new - 32 * gi);
+                float d = group_distance<CH, B>(g, q, mypid[gi], gcount, lane);
+                if ((uint32_t)lane < gcount) keyg[gi] = mk_key(d, mypid[gi]);
+            }
+        }
+
+        // ---- admission (lib.rs:712-719): A = entries with rank_S < ef ----------------------------------
+        const bool full = s.cnt >= ef_cur;
+        const uint64_t furthest = s.cnt ? (near[s.cnt - 1] & kKeyMask) : 0ull;
+        uint32_t rank[ROW_T];
+        bool inA[ROW_T];
+        uint32_t nA = 0;
+#pragma unroll
+        for (int gi = 0; gi < ROW_T; ++gi) {
+            rank[gi] = 0;
+            inA[gi] = false;
+            if (keyg[gi] != kKeyNone && !(full && keyg[gi] > furthest)) {
+                rank[gi] = lower_bound_keys(near, s.cnt, keyg[gi]);
+                inA[gi] = rank[gi] < ef_cur;
+            }
+            nA += __popc(__ballot_sync(kFullMask, inA[gi]));
+        }
+        if (nA == 0) continue;
+
+        // ---- merge S and A into the other buffer: pos = rank among the union ---------------------------
+        uint32_t less[ROW_T];
+        uint32_t shift[EF_T];
+#pragma unroll
+        for (int gi = 0; gi < ROW_T; ++gi) less[gi] = 0;
+#pragma unroll
+        for (int t = 0; t < EF_T; ++t) shift[t] = 0;
+#pragma unroll
+        for (int gi = 0; gi < ROW_T; ++gi) {
+            uint32_t mA = __ballot_sync(kFullMask, inA[gi]);
+            while (mA) {
+                int src = __ffs(mA) - 1;
+                mA &= mA - 1;
+                uint64_t ak = shfl64(keyg[gi], src);
+                uint32_t ar = __shfl_sync(kFullMask, rank[gi], src);
+#pragma unroll
+                for (int g2 = 0; g2 < ROW_T; ++g2) less[g2] += (ak < keyg[g2]) ? 1u : 0u;
+#pragma unroll
+                for (int t = 0; t < EF_T; ++t) shift[t] += (ar <= (uint32_t)(lane + 32 * t)) ? 1u : 0u;
+            }
+        }
+        uint64_t* other = (s.near_base + (s.cur ^ 1) * s.near_len);
+#pragma unroll
+        for (int t = 0; t < EF_T; ++t) {
+            uint32_t idx = lane + 32 * t;
+            if (idx < s.cnt) {
+                uint32_t p = idx + shift[t];
+                if (p < ef_cur) other[p] = near[idx];
+            }
+        }
+#pragma unroll
+        for (int gi = 0; gi < ROW_T; ++gi) {
+            if (inA[gi]) {
+                uint32_t p = rank[gi] + less[gi];
+                if (p < ef_cur) other[p] = keyg[gi];
+            }
+        }
+        __syncwarp();
+        const uint32_t old_cnt = s.cnt;
+        const uint32_t total = old_cnt + nA;
+        s.cnt = min(total, ef_cur);
+        s.cur ^= 1;
+
+        // ---- candidates that fell off the end (lib.rs:612 truncate) -------------------------------------
+        if (total > ef_cur) {
+            const uint32_t fbits = key_dbits(other[ef_cur - 1]);
+            if (s.ntie > 0 && fbits != key_dbits(furthest)) s.ntie = 0;  // their distance is now strictly beyond
+            bool maybe = false;
+#pragma unroll
+            for (int t = 0; t < EF_T; ++t) {
+                uint32_t idx = lane + 32 * t;
+                if (idx < old_cnt && idx + shift[t] >= ef_cur) {
+                    uint64_t k = near[idx];
+                    maybe |= !(k & kFlagExpanded) && key_dbits(k) == fbits;
+                }
+            }
+#pragma unroll
+            for (int gi = 0; gi < ROW_T; ++gi)
+                maybe |= inA[gi] && (rank[gi] + less[gi] >= ef_cur) && key_dbits(keyg[gi]) == fbits;
+            if (__any_sync(kFullMask, maybe))
+                collect_ties<ROW_T, EF_T>(s, near, old_cnt, shift, keyg, rank, inA, less, ef_cur, fbits, lane);
+            if (s.status != kQueryOk) break;
+        }
+    }
+}
+
+// Search::cull (lib.rs:729-737): candidates := nearest; visited := {pids of nearest}.
+template <int EF_T>
+__device__ __forceinline__ void cull(WarpState& s, int lane, bool next_big) {
+    uint64_t* near = (s.near_base + s.cur * s.near_len);
+    s.ntie = 0;
+    vis_clear(s.vis, lane, next_big);
+#pragma unroll
+    for (int t = 0; t < EF_T; ++t) {
+        uint32_t idx = lane + 32 * t;
+        bool have = idx < s.cnt;
+        uint64_t k = have ? near[idx] : 0ull;
+        if (have) near[idx] = k & kKeyMask;                 // every result is a candidate again
+        vis_insert(s.vis, key_pid(k), have);
+    }
+    s.vis.count = s.cnt;
+    __syncwarp();
+}
+
+// Hnsw::search (lib.rs:352-383) when target_layer == 0 and ef_target == ef_search;
+// Construction::insert's descent (lib.rs:443-463) when target_layer = the insert layer, ef_target = ef_construction.
+// Layers above the target are searched on the UpperNode snapshots with ef = 1; the target layer on the zero table.
+// On return nearest = (s.near_base + s.cur * s.near_len)[0..s.cnt).  counters (if non-null): {n_expand_upper, n_dist_upper, n_expand_target, n_dist_target}.
+template <int CH, int ROW_T, int EF_T, int B, bool kLive>
+__device__ __forceinline__ void descend(const GraphView& g, WarpState& s, const float4 (&q)[CH], uint32_t target_layer,
+                                        uint32_t ef_target, int lane, uint32_t* counters4) {
+    s.cur = 0;
+    s.cnt = 0;
+    s.ntie = 0;
+    s.status = kQueryOk;
+    s.n_expand = 0;
+    s.n_dist = 0;
+    s.vis.count = 0;
+    s.vis.use_big = (g.n_upper == target_layer);  // no ef=1 layer above the target: go straight to the big tier
+    uint32_t up_expand = 0, up_dist = 0;
+
+    // push(PointId(0)) (lib.rs:364 / 444)
+    {
+        uint32_t pid0 = 0;
+        vis_insert(s.vis, pid0, lane == 0);
+        s.vis.count = 1;
+        float d = group_distance<CH, B>(g, q, pid0, 1u, lane);
+        if (lane == 0) s.near_base[0] = mk_key(d, pid0);
+        s.cnt = 1;
+        s.n_dist = 1;
+        __syncwarp();
+    }
+    for (uint32_t cur = g.n_upper;; --cur) {
+        if (cur > target_layer) {
+            search_layer<CH, ROW_T, EF_T, B, false>(g, s, q, g.upper[cur - 1], g.M, g.M, 1u, lane);
+            if (s.status != kQueryOk) break;
+            cull<EF_T>(s, lane, /*next_big=*/(cur - 1 == target_layer));
+            up_expand += s.n_expand;
+            up_dist += s.n_dist;
+            s.n_expand = 0;
+            s.n_dist = 0;
+        } else {
+            const uint32_t links = target_layer == 0 ? 2 * g.M : g.M;  // lib.rs:445 / 366-369
+            search_layer<CH, ROW_T, EF_T, B, kLive>(g, s, q, g.zero, 2 * g.M, links, ef_target, lane);
+            break;
+        }
+    }
+    if (counters4 && lane == 0) {
+        counters4[0] = up_expand;
+        counters4[1] = up_dist;
+        counters4[2] = s.n_expand;
+        counters4[3] = s.n_dist;
+    }
+}
+
+// Leave both visited tiers empty for the next query handled by this warp.
+__device__ __forceinline__ void finish_query(WarpState& s, int lane) {
+    vis_clear(s.vis, lane, false);
+}
+
+}  // namespace idb

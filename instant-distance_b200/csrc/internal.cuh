@@ -1,0 +1,99 @@
+// internal.cuh — host-side index object and kernel argument blocks (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/instant_distance_b200.h"
+#include "hnsw_device.cuh"
+
+namespace idb {
+
+constexpr int kSearchWarps = 4;        // warps (= live queries) per CTA
+constexpr int kSearchCtasPerSm = 4;    // resident CTAs per SM -> 16 live queries per SM, <= 128 registers per thread
+constexpr int kRetryWarps = 32;        // warps of the (normally idle) overflow-retry pass
+constexpr uint32_t kRetrySlots = 1u << 21;
+
+extern thread_local char g_err[512];
+idb_status fail(idb_status st, const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t e__ = (expr);                                                                              \
+        if (e__ != cudaSuccess)                                                                                \
+            return ::idb::fail(e__ == cudaErrorMemoryAllocation ? IDB_ERR_OOM : IDB_ERR_CUDA, "CUDA error %s at %s:%d (%s)", \
+                               cudaGetErrorName(e__), __FILE__, __LINE__, cudaGetErrorString(e__));             \
+    } while (0)
+
+struct SearchArgs {
+    GraphView g;
+    const float4* queries;             // nq x nchunks float4 (zero padded rows)
+    unsigned long long n_work;         // number of work items ...
+    const uint32_t* n_work_dev;        // ... or, if non-null, read it from device memory (retry pass)
+    const uint32_t* work_list;         // optional indirection: work item -> query index
+    uint32_t ef, k;
+    uint32_t* out_ids;
+    float* out_dist;
+    uint32_t* out_len;
+    uint32_t* counters;                // nq x 4 u32 or null
+    uint32_t* status;                  // nq
+    unsigned long long* work_counter;
+    uint32_t* fail_count;
+    uint32_t* fail_list;               // may be null (retry pass)
+    uint32_t* vis_tables;
+    uint32_t gslots, gshift;
+    uint64_t* tie_tables;
+};
+
+struct Scratch {
+    uint32_t* vis_tables = nullptr;
+    uint32_t gslots = 0;
+    uint32_t* retry_tables = nullptr;
+    uint64_t* tie_tables = nullptr;
+    unsigned char* ctrl = nullptr;
+    uint32_t* status = nullptr;   size_t status_cap = 0;
+    uint32_t* fail_list = nullptr; size_t fail_cap = 0;
+    uint32_t* counters = nullptr; size_t counters_cap = 0;
+    float* q = nullptr;           size_t q_cap = 0;
+    uint32_t* ids = nullptr;      size_t ids_cap = 0;
+    float* dist = nullptr;        size_t dist_cap = 0;
+    uint32_t* len = nullptr;      size_t len_cap = 0;
+};
+
+struct Index {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+
+    uint64_t n = 0;
+    uint32_t dim = 0, nchunks = 0, M = 32, ef_search = 100;
+    float* d_points = nullptr;                 // n x nchunks*4 f32 (PointId order)
+    uint32_t* d_zero = nullptr;                // n x 2M
+    std::vector<uint32_t*> d_upper;            // [l-1] -> n_l x M
+    std::vector<uint64_t> upper_n;
+    const uint32_t** d_upper_ptrs = nullptr;   // device copy of the pointer table
+
+    Scratch sc;
+    uint64_t last_nq = 0;
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t last_launches = 0;
+
+    ~Index();
+    idb_status init_device(int dev);
+    idb_status upload(const float* points, uint64_t n, uint32_t dim, uint32_t M, uint32_t ef, const uint32_t* zero,
+                      uint32_t n_upper, const uint32_t* const* upper, const uint64_t* upper_n);
+    GraphView view() const;
+    int search_grid() const;
+    idb_status ensure_search_scratch(uint32_t ef, uint64_t nq, uint32_t k);
+    idb_status enqueue_search(const float* d_queries_padded, uint64_t nq, uint32_t ef, uint32_t k, uint32_t* d_ids, float* d_dist,
+                              uint32_t* d_len);
+};
+
+cudaError_t fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t st);
+
+}  // namespace idb

@@ -1,0 +1,95 @@
+// search_kernel.cuh — K1: batched Hnsw::search kernel (lib.rs:352-383 per query) and its launch helpers.
+// Instantiated once per CH (float4 chunks per lane) in search_chN.cu so the translation units build in parallel.
+#pragma once
+#include "internal.cuh"
+
+namespace idb {
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: batched Hnsw::search — persistent grid, one warp per live query, queries claimed from an atomic counter.
+// ---------------------------------------------------------------------------------------------------------
+template <int CH, int ROW_T, int EF_T, int B>
+__global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) search_kernel(SearchArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t gwarp = blockIdx.x * kSearchWarps + warp;
+
+    constexpr int kNearBytes = 2 * 32 * EF_T * 8;
+    constexpr int kWarpBytes = kNearBytes + kSmallVisSlots * 4 + 128 * 4;
+    unsigned char* base = smem_raw + (size_t)warp * kWarpBytes;
+
+    WarpState s;
+    s.near_base = reinterpret_cast<uint64_t*>(base);
+    s.near_len = 32 * EF_T;
+    s.vis.small = reinterpret_cast<uint32_t*>(base + kNearBytes);
+    s.cpid = s.vis.small + kSmallVisSlots;
+    s.vis.big = a.vis_tables + (size_t)gwarp * a.gslots;
+    s.vis.gslots = a.gslots;
+    s.vis.gshift = a.gshift;
+    s.vis.count = 0;
+    s.vis.use_big = false;
+    s.ties = a.tie_tables + (size_t)gwarp * kTieCap;
+    vis_clear_small(s.vis, lane);  // big tables are handed over clean by the host / previous launch
+    const unsigned long long n_work = a.n_work_dev ? (unsigned long long)*a.n_work_dev : a.n_work;
+
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(a.work_counter, 1ull);
+        w = __shfl_sync(kFullMask, w, 0);
+        if (w >= n_work) break;
+        const uint64_t qi = a.work_list ? a.work_list[w] : w;
+
+        float4 q[CH];
+        const float4* qrow = a.queries + qi * a.g.nchunks;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const uint32_t c = lane + 32 * j;
+            q[j] = c < a.g.nchunks ? __ldg(qrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+
+        descend<CH, ROW_T, EF_T, B, false>(a.g, s, q, 0u, a.ef, lane, a.counters ? a.counters + qi * 4 : nullptr);
+
+        const bool ok = s.status == kQueryOk;
+        const uint64_t* near = (s.near_base + s.cur * s.near_len);
+        const uint32_t len = ok ? s.cnt : 0u;
+        for (uint32_t j = lane; j < a.k; j += 32) {
+            uint64_t key = j < len ? near[j] : 0ull;
+            a.out_ids[qi * a.k + j] = j < len ? key_pid(key) : kInvalid;
+            if (a.out_dist) a.out_dist[qi * a.k + j] = j < len ? __uint_as_float(key_dbits(key)) : __int_as_float(0x7f800000);
+        }
+        if (lane == 0) {
+            if (a.out_len) a.out_len[qi] = len;
+            a.status[qi] = s.status;
+            if (!ok) {
+                uint32_t slot = atomicAdd(a.fail_count, 1u);
+                if (a.fail_list) a.fail_list[slot] = (uint32_t)qi;
+            }
+        }
+        finish_query(s, lane);
+    }
+}
+
+template <int CH, int ROW_T, int EF_T, int B>
+static cudaError_t launch_search(const SearchArgs& a, int grid, cudaStream_t stream) {
+    constexpr int kWarpBytes = 2 * 32 * EF_T * 8 + kSmallVisSlots * 4 + 128 * 4;
+    const int smem = kWarpBytes * kSearchWarps;
+    auto kern = search_kernel<CH, ROW_T, EF_T, B>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kSearchWarps * 32, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <int CH, int B>
+cudaError_t dispatch_row_ef(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st) {
+    if (row_t <= 2) {
+        if (ef_t <= 4) return launch_search<CH, 2, 4, B>(a, grid, st);
+        return launch_search<CH, 2, 16, B>(a, grid, st);
+    }
+    if (ef_t <= 4) return launch_search<CH, 4, 4, B>(a, grid, st);
+    return launch_search<CH, 4, 16, B>(a, grid, st);
+}
+
+
+}  // namespace idb

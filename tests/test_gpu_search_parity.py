@@ -1,0 +1,157 @@
+"""GPU parity for the hot path: Hnsw::search (lib.rs:352-383) through the C ABI vs the CPU oracle on the same graph.
+
+Bar (north_star): PointIds bit-identical; distances within 1e-4 relative — here they are required to be
+BIT-IDENTICAL too, because both sides use the same canonical fp32 summation order; so are len(nearest) and the
+traversal counters (expansions / distance evaluations per layer), which proves the traversal itself is identical.
+"""
+import numpy as np
+import pytest
+
+from tests import datagen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def abi():
+    from instant_distance_b200 import _abi
+
+    assert _abi.lib().idb_device_count() >= 1
+    return _abi
+
+
+def _check(abi, oracle, g, ix_o, queries, ef, k=None, counters=True):
+    gpu = abi.Index.from_graph(g.points, g.zero, g.upper, g.M, g.ef_search)
+    k = ef if k is None else k
+    ids, dist, lens = gpu.search(queries, ef_search=ef, k=k)
+    o_ids, o_dist, o_lens, o_cnt = ix_o.search(queries, ef_search=ef, k=k, counters=True)
+    assert (lens == o_lens).all()
+    assert (ids == o_ids).all(), f"{(ids != o_ids).any(axis=1).sum()} of {len(ids)} queries differ"
+    assert dist.tobytes() == o_dist.tobytes()
+    if counters:
+        assert (gpu.last_counters(len(queries)) == o_cnt).all()
+    gpu.close()
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3, 4, 5, 31, 32, 100, 127, 128, 129, 300, 768, 1000])
+def test_distance_bit_exact(abi, oracle, dim):
+    rng = np.random.default_rng(dim)
+    for _ in range(5):
+        a = (rng.standard_normal(dim) * 7).astype(np.float32)
+        b = (rng.standard_normal(dim) * 7).astype(np.float32)
+        assert abi.distance(a, b).tobytes() == oracle.l2sq(a, b).tobytes()
+
+
+def test_map_reference_test_on_gpu(abi, oracle):
+    """tests/all.rs:9-39 with the product metric (squared L2): 0, 2, 2, 8, 8 == (0, 1.4142135, 2.828427)^2."""
+    pts = np.array([[i, i] for i in range(5)], dtype=np.float32)
+    for seed in range(4):
+        ix, ids = oracle.build(pts, seed=seed)
+        g = ix.export()
+        gpu = abi.Index.from_graph(g.points, g.zero, g.upper, g.M)
+        got, dist, lens = gpu.search(np.array([2.0, 2.0], dtype=np.float32))
+        assert lens[0] == 5 and dist[0][:5].tolist() == [0.0, 2.0, 2.0, 8.0, 8.0]
+        assert np.sqrt(dist[0][:5]).astype(np.float32).tolist() == [0.0, np.float32(1.4142135), np.float32(1.4142135),
+                                                                    np.float32(2.828427), np.float32(2.828427)]
+        inv = np.argsort(ids)
+        assert inv[got[0][0]] == 2 and set(inv[got[0][1:3]]) == {1, 3} and set(inv[got[0][3:5]]) == {0, 4}
+        assert (got[0][5:] == 0xFFFFFFFF).all() and np.isinf(dist[0][5:]).all()
+
+
+@pytest.mark.parametrize("n,dim,M,ef", [
+    (1, 8, 32, 10), (2, 8, 32, 10), (20, 3, 32, 100), (1024, 2, 32, 100), (3000, 32, 16, 100), (3000, 32, 24, 100),
+    (5000, 128, 32, 100), (5000, 128, 32, 1), (5000, 128, 32, 7), (5000, 128, 32, 128), (4000, 300, 32, 100),
+    (2000, 768, 32, 64), (3000, 16, 48, 100), (3000, 16, 64, 200), (6000, 64, 32, 300), (6000, 20, 32, 512),
+])
+def test_search_parity_uniform(abi, oracle, n, dim, M, ef):
+    pts = datagen.uniform(n, dim, 100 + n + dim)
+    ix, _ = oracle.build(pts, seed=n, M=M, threads=4)
+    q = datagen.uniform(200, dim, 7)
+    _check(abi, oracle, ix.export(), ix, q, ef)
+
+
+def test_search_parity_10k_x32_config0(abi, oracle):
+    """BASELINE.json configs[0]: 10k x 32, M=16, ef=100, 1k queries."""
+    pts = datagen.uniform(10_000, 32, 42)
+    ix, _ = oracle.build(pts, seed=1, M=16, threads=8)
+    _check(abi, oracle, ix.export(), ix, datagen.uniform(1000, 32, 43), 100, k=10)
+
+
+def test_search_parity_sift_shaped(abi, oracle):
+    pts = datagen.sift_shaped(20_000, 128, 1)
+    ix, _ = oracle.build(pts, seed=3, threads=8)
+    _check(abi, oracle, ix.export(), ix, datagen.sift_shaped(500, 128, 2), 100, k=10)
+
+
+@pytest.mark.parametrize("ef", [1, 2, 10, 100])
+@pytest.mark.parametrize("dim,side", [(3, 12), (2, 6), (8, 2)])
+def test_search_parity_ties_and_duplicates(abi, oracle, ef, dim, side):
+    """Integer grid: exact distance ties and duplicate vectors at the ef boundary (SURVEY §7 hard part 1)."""
+    pts = datagen.grid_ties(3000, dim, 5, side=side)
+    ix, _ = oracle.build(pts, seed=2)
+    _check(abi, oracle, ix.export(), ix, datagen.grid_ties(300, dim, 6, side=side), ef)
+
+
+def test_all_points_identical(abi, oracle):
+    pts = np.ones((500, 4), dtype=np.float32)
+    ix, _ = oracle.build(pts, seed=2)
+    _check(abi, oracle, ix.export(), ix, np.ones((10, 4), dtype=np.float32), 10)
+    _check(abi, oracle, ix.export(), ix, np.zeros((10, 4), dtype=np.float32), 100)
+
+
+def test_empty_index_and_ef_zero(abi, oracle):
+    gpu = abi.Index.from_graph(np.zeros((0, 8), dtype=np.float32), np.zeros((0, 64), dtype=np.uint32), [], 32)
+    ids, dist, lens = gpu.search(np.zeros((3, 8), dtype=np.float32), ef_search=10, k=4)
+    assert (lens == 0).all() and (ids == 0xFFFFFFFF).all() and np.isinf(dist).all()
+    pts = datagen.uniform(100, 8, 1)
+    ix, _ = oracle.build(pts, seed=1)
+    g = ix.export(ef_search=0)
+    gpu = abi.Index.from_graph(g.points, g.zero, g.upper, g.M, 0)
+    ids, dist, lens = gpu.search(pts[:3], ef_search=0, k=4)
+    assert (lens == 0).all() and (ids == 0xFFFFFFFF).all()
+
+
+def test_k_larger_than_result_and_smaller(abi, oracle):
+    pts = datagen.uniform(50, 8, 1)
+    ix, _ = oracle.build(pts, seed=1)
+    g = ix.export()
+    gpu = abi.Index.from_graph(g.points, g.zero, g.upper, g.M)
+    ids, dist, lens = gpu.search(pts[:5], ef_search=100, k=120)
+    assert (lens == 50).all() and (ids[:, 50:] == 0xFFFFFFFF).all() and (ids[:, 0] != 0xFFFFFFFF).all()
+    ids3, _, lens3 = gpu.search(pts[:5], ef_search=100, k=3)
+    assert (ids3 == ids[:, :3]).all() and (lens3 == 50).all()
+
+
+def test_self_query_returns_self_1024x300(abi, oracle):
+    """instant-distance-py/test/test.py:15-35."""
+    emb = np.random.default_rng(5).random((1024, 300), dtype=np.float32)
+    ix, ids = oracle.build(emb, seed=9)
+    g = ix.export()
+    gpu = abi.Index.from_graph(g.points, g.zero, g.upper, g.M)
+    got, dist, _ = gpu.search(emb[123])
+    assert got[0][0] == ids[123] and dist[0][0] == 0.0
+
+
+def test_nan_query_orders_last(abi, oracle):
+    pts = datagen.uniform(300, 8, 1)
+    ix, _ = oracle.build(pts, seed=1)
+    q = datagen.uniform(4, 8, 2)
+    q[1, 3] = np.nan
+    _check(abi, oracle, ix.export(), ix, q, 20)
+
+
+def test_large_batch_and_roundtrip_export(abi, oracle):
+    pts = datagen.uniform(30_000, 64, 77)
+    ix, _ = oracle.build(pts, seed=4, threads=8)
+    g = ix.export()
+    gpu = abi.Index.from_graph(g.points, g.zero, g.upper, g.M)
+    p2, z2, u2 = gpu.export_graph()
+    assert (p2 == g.points).all() and (z2 == g.zero).all() and all((a == b).all() for a, b in zip(u2, g.upper))
+    q = datagen.uniform(20_000, 64, 78)
+    ids, dist, lens = gpu.search(q, ef_search=100, k=10)
+    o_ids, o_dist, o_lens = ix.search(q, ef_search=100, k=10, threads=8)
+    assert (ids == o_ids).all() and dist.tobytes() == o_dist.tobytes() and (lens == o_lens).all()
+    # size-independent properties: sorted by (dist, id), unique ids, idempotent
+    assert (np.diff(dist, axis=1) >= 0).all()
+    ids_b, dist_b, _ = gpu.search(q, ef_search=100, k=10)
+    assert (ids_b == ids).all() and dist_b.tobytes() == dist.tobytes()
