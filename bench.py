@@ -62,50 +62,58 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md), via NVML every ~10 ms."""
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.gpu, self._stop, self.th, self.h, self.nv = [], gpu_index, False, None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml as nv
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            self.h, self.nv = nv.nvmlDeviceGetHandleByIndex(idx), nv
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.th = threading.Thread(target=self._run, daemon=True)
+            self.th.start()
+        except Exception as e:  # noqa: BLE001
+            log("clock sampler unavailable:", e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((time.time(), sm, r, pw))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.01)
 
     def window(self, t0, t1):
-        out = [r for (t, r) in self.rows if t0 - 0.15 <= t <= t1 + 0.15]
-        return out or [r for (_, r) in self.rows[-3:]]
+        out = [r for r in self.rows if t0 <= r[0] <= t1]
+        return out or [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.05] or self.rows[-3:]
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
+        self._stop = True
 
-    @staticmethod
-    def summarize(rows):
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
-            try:
-                sm.append(float(f[0]))
-                mx = max(mx, float(f[1]))
-                for nm, v in zip(names, f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+    def summarize(self, rows):
+        if not rows or self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted({k for k, bit in names.items() for r in rows if r[2] & bit})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(self.max_sm), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(r[3] for r in rows)}
 
 
 def make_workload(args):
@@ -117,14 +125,21 @@ def make_workload(args):
 
 
 def graph_cache_path(args):
-    key = f"{args.n}-{args.dim}-{args.data}-{args.M}-{args.efc}-{args.graph}-v1"
-    d = os.environ.get("IDB_CACHE", "/tmp/idb_cache")
+    key = f"{args.n}-{args.dim}-{args.data}-{args.M}-{args.efc}-{args.graph}-{args.seed}-v2"
+    d = os.environ.get("IDB_CACHE", os.path.join(ROOT, "gpurun_cache"))
     os.makedirs(d, exist_ok=True)
-    return os.path.join(d, hashlib.sha1(key.encode()).hexdigest()[:16] + ".npz")
+    return os.path.join(d, "graph_" + hashlib.sha1(key.encode()).hexdigest()[:16] + ".npz")
+
+
+def permute_points(pts, ids):
+    p = np.empty_like(pts)
+    p[ids] = pts  # points[pid] = rows[orig]   (lib.rs:262-270)
+    return p
 
 
 def obtain_graph(args, pts, device):
-    """Returns (points in PointId order, zero, upper list, how).  Setup, never timed."""
+    """Returns (points in PointId order, zero, upper list, how).  Setup, never timed.
+    The graph (not the points, which are regenerated from the seed) is cached under gpurun_cache/ (git-ignored)."""
     from instant_distance_b200 import _abi
 
     cp = graph_cache_path(args)
@@ -132,13 +147,13 @@ def obtain_graph(args, pts, device):
         z = np.load(cp)
         upper = [z[f"u{i}"] for i in range(int(z["n_upper"]))]
         log(f"graph loaded from cache {cp}")
-        return z["points"], z["zero"], upper, str(z["how"])
+        return permute_points(pts, z["ids"]), z["zero"], upper, str(z["how"]) + " [cached]"
     how = None
     if args.graph == "gpu":
         try:
             t = time.time()
             ix, ids = _abi.Index.build(pts, M=args.M, ef_construction=args.efc, ef_search=args.ef, seed=args.seed, device=device)
-            p, zero, upper = ix.export_graph()
+            _, zero, upper = ix.export_graph()
             ix.close()
             how = f"GPU Builder::build ({time.time() - t:.1f}s)"
         except _abi.IdbError as e:
@@ -152,15 +167,15 @@ def obtain_graph(args, pts, device):
         t = time.time()
         ix, ids = O.build(pts, M=args.M, ef_construction=args.efc, ef_search=args.ef, seed=args.seed, threads=T)
         g = ix.export()
-        p, zero, upper = g.points, g.zero, g.upper
+        zero, upper = g.zero, g.upper
         how = f"oracle (reference algorithm) threaded build, {T} threads ({time.time() - t:.1f}s)"
     log("graph:", how)
     if not args.no_cache:
         try:
-            np.savez(cp, points=p, zero=zero, n_upper=len(upper), how=how, **{f"u{i}": u for i, u in enumerate(upper)})
+            np.savez(cp, ids=ids, zero=zero, n_upper=len(upper), how=how, **{f"u{i}": u for i, u in enumerate(upper)})
         except Exception as e:  # cache is best effort
             log("cache write failed:", e)
-    return p, zero, upper, how
+    return permute_points(pts, ids), zero, upper, how
 
 
 def brute_force_topk_torch(points_dev, queries, k):
@@ -339,7 +354,7 @@ def main():
     if world > 1:
         dist.barrier()
     dev_ms = ev0.elapsed_time(ev1)
-    clocks = ClockSampler.summarize(sampler.window(t_wall0, t_wall1))
+    clocks = sampler.summarize(sampler.window(t_wall0, t_wall1))
 
     # per-launch K1 duration + algorithmic bytes, measured on a second pass (event sync per step would perturb pass 1)
     for s in range(args.warmup, total):

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -91,7 +92,7 @@ static uint32_t next_pow2(uint64_t v) {
 
 idb_status Index::ensure_search_scratch(uint32_t ef, uint64_t nq, uint32_t k) {
     // visited tables: one per resident warp, sized for >= 2x the worst plausible number of visited ids (2M per expansion)
-    uint32_t want_slots = std::max<uint32_t>(1024u, next_pow2(2ull * 2 * M * std::max<uint32_t>(ef, 16u)));
+    uint32_t want_slots = std::max<uint32_t>(1024u, next_pow2((uint64_t)vis_mult * 2 * M * std::max<uint32_t>(ef, 16u)));
     const uint32_t warps = (uint32_t)search_grid() * kSearchWarps;
     if (want_slots > sc.gslots || !sc.vis_tables) {
         if (sc.vis_tables) cudaFree(sc.vis_tables);
@@ -100,6 +101,26 @@ idb_status Index::ensure_search_scratch(uint32_t ef, uint64_t nq, uint32_t k) {
         CUDA_TRY(cudaMalloc(&sc.vis_tables, words * 4));
         CUDA_TRY(fill_u32(sc.vis_tables, words, kInvalid, stream));
         sc.gslots = want_slots;
+        if (l2_persist) {
+            // Keep the per-warp visited tables resident in L2: point rows stream through once, the tables are hit
+            // ~64 times per expansion.  Persisting carve-out + access-policy window on this index's stream.
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+            const size_t bytes = words * 4;
+            const size_t carve = std::min<size_t>(bytes, (size_t)max_persist);
+            if (carve > 0 && max_window > 0) {
+                CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+                cudaStreamAttrValue av;
+                std::memset(&av, 0, sizeof(av));
+                av.accessPolicyWindow.base_ptr = sc.vis_tables;
+                av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)max_window);
+                av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)av.accessPolicyWindow.num_bytes);
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                CUDA_TRY(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
+            }
+        }
     }
     if (!sc.retry_tables) {
         size_t words = (size_t)kRetryWarps * kRetrySlots;
@@ -115,7 +136,7 @@ idb_status Index::ensure_search_scratch(uint32_t ef, uint64_t nq, uint32_t k) {
     return IDB_OK;
 }
 
-int Index::search_grid() const { return num_sms * kSearchCtasPerSm; }
+int Index::search_grid() const { return num_sms * ctas_per_sm; }
 
 // Enqueue one batched search; all pointers are device pointers, d_queries padded to nchunks*4 floats per row.
 idb_status Index::enqueue_search(const float* d_queries_padded, uint64_t nq, uint32_t ef, uint32_t k, uint32_t* d_ids,
@@ -186,6 +207,7 @@ GraphView Index::view() const {
     g.n_upper = (uint32_t)d_upper.size();
     g.M = M;
     g.n = n;
+    g.flags = opt_flags;
     return g;
 }
 
@@ -227,6 +249,10 @@ idb_status Index::init_device(int dev) {
         return fail(IDB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
     num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (const char* e = std::getenv("IDB_OPT")) opt_flags = (uint32_t)std::atoi(e);
+    if (const char* e = std::getenv("IDB_VIS_MULT")) vis_mult = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("IDB_L2_PERSIST")) l2_persist = std::atoi(e) != 0;
+    if (const char* e = std::getenv("IDB_CTAS_PER_SM")) ctas_per_sm = std::min(kSearchCtasPerSm, std::max(1, std::atoi(e)));
     return IDB_OK;
 }
 
@@ -298,13 +324,6 @@ idb_status idb_params_default(idb_params* p) {
     p->insert_batch = 0;
     p->device = 0;
     return IDB_OK;
-}
-
-idb_status idb_build_f32(const float* rows, uint64_t n, uint32_t dim, const idb_params* params, idb_index** out_index,
-                         uint32_t* out_ids) {
-    (void)rows; (void)n; (void)dim; (void)params; (void)out_ids;
-    if (out_index) *out_index = nullptr;
-    return fail(IDB_ERR_UNSUPPORTED, "GPU build is not implemented yet");
 }
 
 idb_status idb_index_from_graph_f32(const float* points, uint64_t n, uint32_t dim, uint32_t M, uint32_t ef_search,

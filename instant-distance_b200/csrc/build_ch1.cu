@@ -1,0 +1,5 @@
+// Construction kernels (KA insert search, K2 select/relink) for rows of up to 128 floats.
+#include "build_dispatch.cuh"
+namespace idb {
+cudaError_t build_dispatch_ch1(const BuildArgs& a, const BuildLaunch& l, cudaStream_t st) { return build_dispatch<1, 16, 16>(a, l, st); }
+}  // namespace idb

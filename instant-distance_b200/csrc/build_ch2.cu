@@ -1,0 +1,5 @@
+// Construction kernels (KA insert search, K2 select/relink) for rows of up to 256 floats.
+#include "build_dispatch.cuh"
+namespace idb {
+cudaError_t build_dispatch_ch2(const BuildArgs& a, const BuildLaunch& l, cudaStream_t st) { return build_dispatch<2, 8, 8>(a, l, st); }
+}  // namespace idb

@@ -1,0 +1,65 @@
+// build_dispatch.cuh — launch helpers for the construction kernels, instantiated once per CH in build_chN.cu.
+#pragma once
+#include "build_kernels.cuh"
+
+namespace idb {
+
+enum BuildOp : int { kOpInsertSearch = 0, kOpSelectNew = 1, kOpRelink = 2, kOpRelinkSimple = 3 };
+
+struct BuildLaunch {
+    BuildOp op;
+    int row_t, ef_t;        // KA template selectors
+    bool stage;             // K2: kept rows staged in shared memory
+    int grid;
+    uint32_t smem_per_warp; // K2
+};
+
+template <int CH, int ROW_T, int EF_T, int B>
+cudaError_t launch_insert_search(const BuildArgs& a, int grid, cudaStream_t st) {
+    constexpr int kWarpBytes = 2 * 32 * EF_T * 8 + kSmallVisSlots * 4 + 128 * 4 + 128 * 8;
+    const int smem = kWarpBytes * kSearchWarps;
+    auto kern = insert_search_kernel<CH, ROW_T, EF_T, B>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kSearchWarps * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int CH, int NB, bool kStage>
+cudaError_t launch_k2(const BuildArgs& a, const BuildLaunch& l, cudaStream_t st) {
+    const int smem = (int)l.smem_per_warp * kBuildWarps;
+    if (l.op == kOpSelectNew) {
+        auto kern = select_new_kernel<CH, NB, kStage>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        kern<<<l.grid, kBuildWarps * 32, smem, st>>>(a, l.smem_per_warp);
+    } else {
+        auto kern = relink_kernel<CH, NB, kStage>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        kern<<<l.grid, kBuildWarps * 32, smem, st>>>(a, l.smem_per_warp);
+    }
+    return cudaGetLastError();
+}
+
+template <int CH, int B, int NB>
+cudaError_t build_dispatch(const BuildArgs& a, const BuildLaunch& l, cudaStream_t st) {
+    switch (l.op) {
+        case kOpInsertSearch:
+            if (l.row_t <= 2) {
+                if (l.ef_t <= 4) return launch_insert_search<CH, 2, 4, B>(a, l.grid, st);
+                return launch_insert_search<CH, 2, 16, B>(a, l.grid, st);
+            }
+            if (l.ef_t <= 4) return launch_insert_search<CH, 4, 4, B>(a, l.grid, st);
+            return launch_insert_search<CH, 4, 16, B>(a, l.grid, st);
+        case kOpSelectNew:
+        case kOpRelink:
+            return l.stage ? launch_k2<CH, NB, true>(a, l, st) : launch_k2<CH, NB, false>(a, l, st);
+        case kOpRelinkSimple:
+            relink_simple_kernel<CH><<<l.grid, kBuildWarps * 32, 0, st>>>(a);
+            return cudaGetLastError();
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace idb

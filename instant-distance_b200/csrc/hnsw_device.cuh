@@ -31,6 +31,8 @@ constexpr int kSmallVisSlots = 512;           // shared-memory visited set used 
 constexpr int kTieCap = 1024;                 // per-warp tie list capacity (global memory)
 constexpr uint32_t kFullMask = 0xFFFFFFFFu;
 
+enum OptFlags : uint32_t { kOptPrefetchVectors = 1u, kOptPrefetchRows = 2u };
+
 enum QueryStatus : uint32_t { kQueryOk = 0, kQueryVisitedOverflow = 1, kQueryTieOverflow = 2 };
 
 struct GraphView {
@@ -41,12 +43,13 @@ struct GraphView {
     uint32_t n_upper;
     uint32_t M;
     uint64_t n;
+    uint32_t flags;              // kOpt* tuning switches (never change results)
 };
 
 // ---------------------------------------------------------------------------------------------------------
 // Canonical squared-L2 (DESIGN.md "canonical distance"; the CPU checker restates the same order):
 //   lane l owns float4 chunks l, l+32, l+64, ...; four fmaf chains (one per float4 component);
-//   lane sum (a0+a1)+(a2+a3); xor butterfly over lanes with offsets 16, 8, 4, 2, 1.
+//   lane sum (a0+a1)+(a2+a3); xor butterfly over lanes with offsets 1, 2, 4, 8, 16.
 // ---------------------------------------------------------------------------------------------------------
 template <int CH>
 __device__ __forceinline__ float lane_partial(const float4 (&q)[CH], const float4 (&v)[CH]) {
@@ -63,29 +66,37 @@ __device__ __forceinline__ float lane_partial(const float4 (&q)[CH], const float
     return __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
 }
 
-// Butterfly for ONE vector: every lane ends with the total.
+// Butterfly for ONE vector (offsets 1, 2, 4, 8, 16 — the canonical order): every lane ends with the total.
 __device__ __forceinline__ float butterfly_sum(float s) {
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) s = __fadd_rn(s, __shfl_xor_sync(kFullMask, s, off));
+    for (int off = 1; off <= 16; off <<= 1) s = __fadd_rn(s, __shfl_xor_sync(kFullMask, s, off));
     return s;
 }
 
-// Butterfly for 32 vectors at once ("transposing" reduction, 31 shuffles instead of 160): p[i] is this lane's
-// partial for vector i; on return lane l holds the total of vector l.  Same add tree as butterfly_sum.
-__device__ __forceinline__ float transpose_reduce32(float (&p)[32], int lane) {
-#define IDB_TR_STAGE(OFF)                                                        \
-    {                                                                            \
-        const bool up = (lane & OFF) != 0;                                       \
-        _Pragma("unroll") for (int i = 0; i < OFF; ++i) {                        \
-            float send = up ? p[i] : p[i + OFF];                                 \
-            float keep = up ? p[i + OFF] : p[i];                                 \
-            p[i] = __fadd_rn(keep, __shfl_xor_sync(kFullMask, send, OFF));       \
-        }                                                                        \
+// Butterfly for NB (power of two <= 32) vectors at once: p[i] is this lane's partial for vector i.  The first
+// log2(NB) stages are "transposing" (each lane hands half of its values to its partner and keeps the other half,
+// split by even/odd index), so NB vectors cost NB-1 shuffles instead of 5*NB; the remaining stages are plain.
+// Same add tree as butterfly_sum for every vector.  On return lane l holds the total of vector (l & (NB-1)).
+template <int NB>
+__device__ __forceinline__ float batch_butterfly(float (&p)[NB], int lane) {
+    int off = 1;
+#pragma unroll
+    for (int m = NB; m > 1; m >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < m / 2; ++i) {
+            float send = up ? p[2 * i] : p[2 * i + 1];
+            float keep = up ? p[2 * i + 1] : p[2 * i];
+            p[i] = __fadd_rn(keep, __shfl_xor_sync(kFullMask, send, off));
+        }
+        off <<= 1;
     }
-    IDB_TR_STAGE(16) IDB_TR_STAGE(8) IDB_TR_STAGE(4) IDB_TR_STAGE(2) IDB_TR_STAGE(1)
-#undef IDB_TR_STAGE
+#pragma unroll
+    for (int o = NB; o <= 16; o <<= 1) p[0] = __fadd_rn(p[0], __shfl_xor_sync(kFullMask, p[0], o));
     return p[0];
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ uint32_t canon_bits(float d) {
     uint32_t b = __float_as_uint(d);
@@ -188,6 +199,7 @@ struct WarpState {
     uint64_t* near_base;     // shared: two buffers of near_len keys each (ping-pong for the merge)
     uint32_t near_len;       // 32*EF_T
     uint32_t* cpid;          // shared: 128 compacted new ids of the current row
+    uint64_t* ckey;          // shared: their 128 keys (canonical distance bits << 32 | pid)
     uint64_t* ties;          // global: kTieCap keys
     int cur;                 // live near buffer
     uint32_t cnt;            // len(nearest)
@@ -206,35 +218,39 @@ __device__ __forceinline__ uint32_t lower_bound_keys(const uint64_t* a, uint32_t
     return lo;
 }
 
-// Distances from q to the (<= 32) points whose ids sit one per lane in `mypid` (lanes >= gcount: ignored).
-// Lane l returns the canonical squared-L2 to point mypid@lane l.
-template <int CH, int B>
-__device__ __forceinline__ float group_distance(const GraphView& g, const float4 (&q)[CH], uint32_t mypid, uint32_t gcount,
-                                                int lane) {
-    float p[32];
-#pragma unroll
-    for (int b = 0; b < 32; b += B) {
-        if ((uint32_t)b < gcount) {  // warp-uniform
-            float4 v[B][CH];
-#pragma unroll
-            for (int i = 0; i < B; ++i) {
-                uint32_t pid = __shfl_sync(kFullMask, mypid, b + i);
-                const bool ok = (uint32_t)(b + i) < gcount;
-                const float4* row = g.points + (size_t)pid * g.nchunks;
-#pragma unroll
-                for (int j = 0; j < CH; ++j) {
-                    const uint32_t c = lane + 32 * j;
-                    v[i][j] = (ok && c < g.nchunks) ? __ldg(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < B; ++i) p[b + i] = lane_partial<CH>(q, v[i]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < B; ++i) p[b + i] = 0.f;
+// Distances from q to the n_new points listed in s.cpid (shared), NB rows in flight per lane; writes the keys
+// (canonical distance bits << 32 | pid) to s.ckey.  The only place in the traversal that touches point rows.
+template <int CH, int NB>
+__device__ __forceinline__ void batch_distances(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid, uint64_t* ckey,
+                                                uint32_t n_new, int lane) {
+    if (g.flags & kOptPrefetchVectors) {  // pull every row of this expansion into L2 now; the batches below then hit L2
+        const uint32_t lines = (g.nchunks + 7) / 8;  // 128-byte lines per row
+        for (uint32_t t = lane; t < n_new * lines; t += 32) {
+            const uint32_t c = t / lines, ln = t - c * lines;
+            prefetch_l2(g.points + (size_t)cpid[c] * g.nchunks + ln * 8);
         }
     }
-    return transpose_reduce32(p, lane);
+#pragma unroll 1
+    for (uint32_t b0 = 0; b0 < n_new; b0 += NB) {
+        float4 v[NB][CH];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const bool ok = b0 + i < n_new;
+            const uint32_t pid = ok ? cpid[b0 + i] : 0u;  // shared-memory broadcast
+            const float4* row = g.points + (size_t)pid * g.nchunks;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const uint32_t c = lane + 32 * j;
+                v[i][j] = (ok && c < g.nchunks) ? __ldg(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        float p[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) p[i] = lane_partial<CH>(q, v[i]);
+        const float total = batch_butterfly<NB>(p, lane);
+        if (lane < NB && b0 + lane < n_new) ckey[b0 + lane] = mk_key(total, cpid[b0 + lane]);
+    }
+    __syncwarp();
 }
 
 // Rare path: something was evicted while its distance equals the new furthest distance.  Such an entry stays a
@@ -322,91 +338,85 @@ __device__ __forceinline__ uint64_t pop_min_tie(WarpState& s, int lane) {
 // ---------------------------------------------------------------------------------------------------------
 template <int CH, int ROW_T, int EF_T, int B, bool kLive>
 __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, const float4 (&q)[CH], const uint32_t* rows,
-                                             uint32_t width, uint32_t links, uint32_t ef_cur, int lane) {
+                                             uint32_t width, uint32_t links, uint32_t ef_cur, bool seed_entry, int lane) {
     const uint32_t lt_mask = (1u << lane) - 1;
     for (;;) {
         uint64_t* near = (s.near_base + s.cur * s.near_len);
-        // ---- pop the min candidate: first unexpanded entry of nearest, else the smallest tie ----------
-        int sel = -1;
-#pragma unroll
-        for (int t = 0; t < EF_T; ++t) {
-            if (sel < 0) {
-                uint32_t idx = lane + 32 * t;
-                bool un = idx < s.cnt && !(near[idx] & kFlagExpanded);
-                uint32_t m = __ballot_sync(kFullMask, un);
-                if (m) sel = 32 * t + __ffs(m) - 1;
-            }
-        }
-        uint32_t cpid;
-        if (sel >= 0) {
-            uint64_t ck = near[sel];
-            cpid = key_pid(ck);
-            __syncwarp();
-            if (lane == 0) near[sel] = ck | kFlagExpanded;
-            __syncwarp();
-        } else if (s.ntie > 0) {
-            cpid = key_pid(pop_min_tie(s, lane));  // dist == furthest dist by invariant -> not `>` -> expanded
-        } else {
-            break;  // heap empty, or its min is strictly beyond the furthest result (lib.rs:601-603)
-        }
-        s.n_expand++;
-
-        // ---- row of the candidate: NearestIter stops at the first INVALID (types.rs:178-191) ----------
-        uint32_t ent[ROW_T];
-        const uint32_t* row = rows + (size_t)cpid * width;
-#pragma unroll
-        for (int t = 0; t < ROW_T; ++t) {
-            uint32_t e = lane + 32 * t;
-            ent[t] = kInvalid;
-            if (e < links) ent[t] = kLive ? __ldcg(row + e) : __ldg(row + e);
-        }
-        uint32_t count = 32 * ROW_T;
-#pragma unroll
-        for (int t = ROW_T - 1; t >= 0; --t) {
-            uint32_t m = __ballot_sync(kFullMask, ent[t] == kInvalid);
-            if (m) count = 32 * t + __ffs(m) - 1;
-        }
-        if (count == 0) continue;
-
-        // ---- visited.insert for every row entry (lib.rs:705) -------------------------------------------
-        if (!vis_reserve(s.vis, count, lane)) { s.status = kQueryVisitedOverflow; break; }
-        bool isnew[ROW_T];
-        uint32_t cpos[ROW_T];
         uint32_t n_new = 0;
+        if (seed_entry) {
+            // push(PointId(0)) (lib.rs:364 / 444): the entry point is the only "row entry" of a pseudo expansion
+            seed_entry = false;
+            vis_insert(s.vis, 0u, lane == 0);
+            s.vis.count = 1;
+            if (lane == 0) s.cpid[0] = 0u;
+            n_new = 1;
+            s.n_dist += 1;
+            __syncwarp();
+        } else {
+            // ---- pop the min candidate: first unexpanded entry of nearest, else the smallest tie ----------
+            int sel = -1;
 #pragma unroll
-        for (int t = 0; t < ROW_T; ++t) {
-            isnew[t] = vis_insert(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count);
-            uint32_t m = __ballot_sync(kFullMask, isnew[t]);
-            cpos[t] = n_new + __popc(m & lt_mask);
-            n_new += __popc(m);
-        }
-        s.vis.count += n_new;
-        s.n_dist += n_new;
-        if (n_new == 0) continue;
+            for (int t = 0; t < EF_T; ++t) {
+                if (sel < 0) {
+                    uint32_t idx = lane + 32 * t;
+                    bool un = idx < s.cnt && !(near[idx] & kFlagExpanded);
+                    uint32_t m = __ballot_sync(kFullMask, un);
+                    if (m) sel = 32 * t + __ffs(m) - 1;
+                }
+            }
+            uint32_t cpid;
+            if (sel >= 0) {
+                uint64_t ck = near[sel];
+                cpid = key_pid(ck);
+                __syncwarp();
+                if (lane == 0) near[sel] = ck | kFlagExpanded;
+                __syncwarp();
+            } else if (s.ntie > 0) {
+                cpid = key_pid(pop_min_tie(s, lane));  // dist == furthest dist by invariant -> not `>` -> expanded
+            } else {
+                break;  // heap empty, or its min is strictly beyond the furthest result (lib.rs:601-603)
+            }
+            s.n_expand++;
 
-        // ---- compact the new ids in row order, one per lane per group of 32 ----------------------------
+            // ---- row of the candidate: NearestIter stops at the first INVALID (types.rs:178-191) ----------
+            uint32_t ent[ROW_T];
+            const uint32_t* row = rows + (size_t)cpid * width;
 #pragma unroll
-        for (int t = 0; t < ROW_T; ++t)
-            if (isnew[t]) s.cpid[cpos[t]] = ent[t];
-        __syncwarp();
-        uint32_t mypid[ROW_T];
+            for (int t = 0; t < ROW_T; ++t) {
+                uint32_t e = lane + 32 * t;
+                ent[t] = kInvalid;
+                if (e < links) ent[t] = kLive ? __ldcg(row + e) : __ldg(row + e);
+            }
+            uint32_t count = 32 * ROW_T;
+#pragma unroll
+            for (int t = ROW_T - 1; t >= 0; --t) {
+                uint32_t m = __ballot_sync(kFullMask, ent[t] == kInvalid);
+                if (m) count = 32 * t + __ffs(m) - 1;
+            }
+            if (count == 0) continue;
+
+            // ---- visited.insert for every row entry (lib.rs:705), compacted in row order ------------------
+            if (!vis_reserve(s.vis, count, lane)) { s.status = kQueryVisitedOverflow; break; }
+#pragma unroll
+            for (int t = 0; t < ROW_T; ++t) {
+                const bool fresh = vis_insert(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count);
+                const uint32_t m = __ballot_sync(kFullMask, fresh);
+                if (fresh) s.cpid[n_new + __popc(m & lt_mask)] = ent[t];
+                n_new += __popc(m);
+            }
+            s.vis.count += n_new;
+            s.n_dist += n_new;
+            if (n_new == 0) continue;
+            __syncwarp();
+        }
+
+        // ---- distances (lib.rs:709-710) --------------------------------------------------------------------
+        batch_distances<CH, B>(g, q, s.cpid, s.ckey, n_new, lane);
         uint64_t keyg[ROW_T];
 #pragma unroll
         for (int gi = 0; gi < ROW_T; ++gi) {
-            uint32_t c = 32 * gi + lane;
-            mypid[gi] = c < n_new ? s.cpid[c] : 0u;
-            keyg[gi] = kKeyNone;
-        }
-        __syncwarp();
-
-        // ---- distances (lib.rs:709-710), 32 rows per group ---------------------------------------------
-#pragma unroll
-        for (int gi = 0; gi < ROW_T; ++gi) {
-            if ((uint32_t)(32 * gi) < n_new) {
-                uint32_t gcount = min(32u, n_new - 32 * gi);
-                float d = group_distance<CH, B>(g, q, mypid[gi], gcount, lane);
-                if ((uint32_t)lane < gcount) keyg[gi] = mk_key(d, mypid[gi]);
-            }
+            const uint32_t c = 32 * gi + lane;
+            keyg[gi] = c < n_new ? s.ckey[c] : kKeyNone;
         }
 
         // ---- admission (lib.rs:712-719): A = entries with rank_S < ef ----------------------------------
@@ -461,7 +471,14 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
         for (int gi = 0; gi < ROW_T; ++gi) {
             if (inA[gi]) {
                 uint32_t p = rank[gi] + less[gi];
-                if (p < ef_cur) other[p] = keyg[gi];
+                if (p < ef_cur) {
+                    other[p] = keyg[gi];
+                    if (g.flags & kOptPrefetchRows) {  // it will most likely be expanded: start fetching its adjacency row
+                        const uint32_t* r = rows + (size_t)key_pid(keyg[gi]) * width;
+                        prefetch_l2(r);
+                        if (links > 32) prefetch_l2(r + 32);
+                    }
+                }
             }
         }
         __syncwarp();
@@ -528,31 +545,20 @@ __device__ __forceinline__ void descend(const GraphView& g, WarpState& s, const 
     s.vis.use_big = (g.n_upper == target_layer);  // no ef=1 layer above the target: go straight to the big tier
     uint32_t up_expand = 0, up_dist = 0;
 
-    // push(PointId(0)) (lib.rs:364 / 444)
-    {
-        uint32_t pid0 = 0;
-        vis_insert(s.vis, pid0, lane == 0);
-        s.vis.count = 1;
-        float d = group_distance<CH, B>(g, q, pid0, 1u, lane);
-        if (lane == 0) s.near_base[0] = mk_key(d, pid0);
-        s.cnt = 1;
-        s.n_dist = 1;
-        __syncwarp();
-    }
+    bool seed = true;  // push(PointId(0)) (lib.rs:364 / 444) happens inside the first search_layer call
     for (uint32_t cur = g.n_upper;; --cur) {
-        if (cur > target_layer) {
-            search_layer<CH, ROW_T, EF_T, B, false>(g, s, q, g.upper[cur - 1], g.M, g.M, 1u, lane);
-            if (s.status != kQueryOk) break;
-            cull<EF_T>(s, lane, /*next_big=*/(cur - 1 == target_layer));
-            up_expand += s.n_expand;
-            up_dist += s.n_dist;
-            s.n_expand = 0;
-            s.n_dist = 0;
-        } else {
-            const uint32_t links = target_layer == 0 ? 2 * g.M : g.M;  // lib.rs:445 / 366-369
-            search_layer<CH, ROW_T, EF_T, B, kLive>(g, s, q, g.zero, 2 * g.M, links, ef_target, lane);
-            break;
-        }
+        const bool above = cur > target_layer;
+        const uint32_t* rows = above ? g.upper[cur - 1] : g.zero;
+        const uint32_t width = above ? g.M : 2 * g.M;
+        const uint32_t links = (above || target_layer != 0) ? g.M : 2 * g.M;  // lib.rs:445 / 366-369
+        search_layer<CH, ROW_T, EF_T, B, kLive>(g, s, q, rows, width, links, above ? 1u : ef_target, seed, lane);
+        seed = false;
+        if (!above || s.status != kQueryOk) break;
+        cull<EF_T>(s, lane, /*next_big=*/(cur - 1 == target_layer));
+        up_expand += s.n_expand;
+        up_dist += s.n_dist;
+        s.n_expand = 0;
+        s.n_dist = 0;
     }
     if (counters4 && lane == 0) {
         counters4[0] = up_expand;

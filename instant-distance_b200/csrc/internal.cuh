@@ -79,6 +79,11 @@ struct Index {
 
     Scratch sc;
     uint64_t last_nq = 0;
+    // tuning knobs (env IDB_OPT / IDB_VIS_MULT / IDB_L2_PERSIST / IDB_CTAS_PER_SM); none of them changes results
+    uint32_t opt_flags = kOptPrefetchVectors | kOptPrefetchRows;
+    uint32_t vis_mult = 2;        // visited table slots = next_pow2(vis_mult * 2M * ef)
+    bool l2_persist = false;      // pin the visited tables in L2 with an access-policy window
+    int ctas_per_sm = kSearchCtasPerSm;
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t last_launches = 0;

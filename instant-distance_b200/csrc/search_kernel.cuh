@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) search_ke
     const uint32_t gwarp = blockIdx.x * kSearchWarps + warp;
 
     constexpr int kNearBytes = 2 * 32 * EF_T * 8;
-    constexpr int kWarpBytes = kNearBytes + kSmallVisSlots * 4 + 128 * 4;
+    constexpr int kWarpBytes = kNearBytes + kSmallVisSlots * 4 + 128 * 4 + 128 * 8;
     unsigned char* base = smem_raw + (size_t)warp * kWarpBytes;
 
     WarpState s;
@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) search_ke
     s.near_len = 32 * EF_T;
     s.vis.small = reinterpret_cast<uint32_t*>(base + kNearBytes);
     s.cpid = s.vis.small + kSmallVisSlots;
+    s.ckey = reinterpret_cast<uint64_t*>(s.cpid + 128);
     s.vis.big = a.vis_tables + (size_t)gwarp * a.gslots;
     s.vis.gslots = a.gslots;
     s.vis.gshift = a.gshift;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) search_ke
 
 template <int CH, int ROW_T, int EF_T, int B>
 static cudaError_t launch_search(const SearchArgs& a, int grid, cudaStream_t stream) {
-    constexpr int kWarpBytes = 2 * 32 * EF_T * 8 + kSmallVisSlots * 4 + 128 * 4;
+    constexpr int kWarpBytes = 2 * 32 * EF_T * 8 + kSmallVisSlots * 4 + 128 * 4 + 128 * 8;
     const int smem = kWarpBytes * kSearchWarps;
     auto kern = search_kernel<CH, ROW_T, EF_T, B>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -52,7 +52,7 @@ constexpr uint32_t INVALID = 0xFFFFFFFFu;  // types:293
 // Canonical squared-L2 (shared with the GPU kernels, see DESIGN.md "canonical distance").
 //   128 accumulators acc[i mod 128], each an fmaf chain over i = r, r+128, r+256, ... (ascending);
 //   lane sums s[l] = (acc[4l]+acc[4l+1]) + (acc[4l+2]+acc[4l+3]), l = 0..31;
-//   xor butterfly over l with offsets 16, 8, 4, 2, 1:  s[l] <- s[l] + s[l^off];  result s[0].
+//   xor butterfly over l with offsets 1, 2, 4, 8, 16:  s[l] <- s[l] + s[l^off];  result s[0].
 // ---------------------------------------------------------------------------------------------
 float l2sq_canonical_scalar(const float* q, const float* x, uint32_t dim) {
     float acc[128];
@@ -63,7 +63,7 @@ float l2sq_canonical_scalar(const float* q, const float* x, uint32_t dim) {
     }
     float s[32], t[32];
     for (int l = 0; l < 32; ++l) s[l] = (acc[4 * l] + acc[4 * l + 1]) + (acc[4 * l + 2] + acc[4 * l + 3]);
-    for (int off = 16; off >= 1; off >>= 1) {
+    for (int off = 1; off <= 16; off <<= 1) {
         for (int l = 0; l < 32; ++l) t[l] = s[l] + s[l ^ off];
         for (int l = 0; l < 32; ++l) s[l] = t[l];
     }
@@ -104,13 +104,16 @@ __attribute__((target("avx512f,avx512dq,fma"))) float l2sq_canonical_avx512(cons
     }
     ORC_QUAD(a0) ORC_QUAD(a1) ORC_QUAD(a2) ORC_QUAD(a3) ORC_QUAD(a4) ORC_QUAD(a5) ORC_QUAD(a6) ORC_QUAD(a7)
 #undef ORC_QUAD
-    // zmm k holds lanes l = 4k..4k+3 (each x4).  butterfly off=16 <-> k^4, off=8 <-> k^2, off=4 <-> k^1
-    a0 = _mm512_add_ps(a0, a4); a1 = _mm512_add_ps(a1, a5); a2 = _mm512_add_ps(a2, a6); a3 = _mm512_add_ps(a3, a7);
-    a0 = _mm512_add_ps(a0, a2); a1 = _mm512_add_ps(a1, a3);
-    a0 = _mm512_add_ps(a0, a1);
-    // off=2 <-> 128-bit lane m^2, off=1 <-> m^1
-    a0 = _mm512_add_ps(a0, _mm512_shuffle_f32x4(a0, a0, 0x4E));
-    a0 = _mm512_add_ps(a0, _mm512_shuffle_f32x4(a0, a0, 0xB1));
+    // zmm k holds lanes l = 4k+m, m = 128-bit lane index (each value x4).
+    // butterfly off=1 <-> m^1, off=2 <-> m^2 (in-register lane swaps), off=4 <-> k^1, off=8 <-> k^2, off=16 <-> k^4
+#define ORC_BF(V)                                                 \
+    V = _mm512_add_ps(V, _mm512_shuffle_f32x4(V, V, 0xB1));       \
+    V = _mm512_add_ps(V, _mm512_shuffle_f32x4(V, V, 0x4E));
+    ORC_BF(a0) ORC_BF(a1) ORC_BF(a2) ORC_BF(a3) ORC_BF(a4) ORC_BF(a5) ORC_BF(a6) ORC_BF(a7)
+#undef ORC_BF
+    a0 = _mm512_add_ps(a0, a1); a2 = _mm512_add_ps(a2, a3); a4 = _mm512_add_ps(a4, a5); a6 = _mm512_add_ps(a6, a7);
+    a0 = _mm512_add_ps(a0, a2); a4 = _mm512_add_ps(a4, a6);
+    a0 = _mm512_add_ps(a0, a4);
     return _mm512_cvtss_f32(a0);
 }
 #endif

@@ -1,0 +1,71 @@
+"""Sweeps the K1 tuning knobs (env vars read at index creation) on one graph; prints kernel ms per config.
+Usage (GPU box): python scripts/tune_search.py --n 1000000 [--configs "OPT,VIS,L2P,CTAS;..."]"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+import bench  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=1_000_000)
+ap.add_argument("--dim", type=int, default=128)
+ap.add_argument("--ef", type=int, default=100)
+ap.add_argument("--efc", type=int, default=100)
+ap.add_argument("--M", type=int, default=32)
+ap.add_argument("--seed", type=int, default=20260923)
+ap.add_argument("--data", default="sift")
+ap.add_argument("--graph", default="oracle")
+ap.add_argument("--batch", type=int, default=10000)
+ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--configs", default="0,2,0,4;1,2,0,4;2,2,0,4;3,2,0,4;3,1,0,4;3,2,1,4;3,1,1,4;3,2,0,3;3,2,0,2")
+args = ap.parse_args()
+args.no_cache = False
+
+import torch  # noqa: E402
+
+from instant_distance_b200 import _abi  # noqa: E402
+
+pts, gen = bench.make_workload(args)
+try:
+    p, zero, upper, how = bench.obtain_graph(args, pts, 0)
+except Exception as e:  # noqa: BLE001  (e.g. the GPU build failed: fall back to a smaller oracle-built graph)
+    print("graph via", args.graph, "failed:", e, file=sys.stderr)
+    args.graph, args.n = "oracle", min(args.n, 300_000)
+    pts, gen = bench.make_workload(args)
+    p, zero, upper, how = bench.obtain_graph(args, pts, 0)
+print(json.dumps({"graph": how, "n": args.n}), flush=True)
+del pts
+qs = [torch.from_numpy(gen(args.batch, args.dim, 7000 + s)).cuda() for s in range(args.steps + 2)]
+k = 10
+d_ids = torch.empty((args.batch, k), dtype=torch.int32, device="cuda")
+d_dist = torch.empty((args.batch, k), dtype=torch.float32, device="cuda")
+d_len = torch.empty((args.batch,), dtype=torch.int32, device="cuda")
+ref_ids = None
+results = []
+for cfg in args.configs.split(";"):
+    opt, vis, l2p, ctas = cfg.split(",")
+    os.environ.update({"IDB_OPT": opt, "IDB_VIS_MULT": vis, "IDB_L2_PERSIST": l2p, "IDB_CTAS_PER_SM": ctas})
+    ix = _abi.Index.from_graph(p, zero, upper, args.M, args.ef)
+    ix.set_profiling(True)
+    ms = []
+    for s in range(args.steps + 2):
+        ix.search_device(qs[s].data_ptr(), args.batch, args.ef, k, d_ids.data_ptr(), d_dist.data_ptr(), d_len.data_ptr())
+        t, _ = ix.last_kernel_ms()
+        if s >= 2:
+            ms.append(t)
+    ids = d_ids.cpu().numpy()
+    if ref_ids is None:
+        ref_ids = ids
+    same = bool((ids == ref_ids).all())
+    byts = float(bench.algorithmic_bytes(ix.last_counters(args.batch), args.dim, args.M, k).sum())
+    r = {"opt": int(opt), "vis_mult": int(vis), "l2_persist": int(l2p), "ctas_per_sm": int(ctas), "kernel_ms": float(np.mean(ms)),
+         "min_ms": float(np.min(ms)), "GBps": byts / (np.mean(ms) / 1e3) / 1e9, "qps": args.batch / (np.mean(ms) / 1e3), "same_ids": same}
+    print(json.dumps(r), flush=True)
+    results.append(r)
+    ix.close()
+    torch.cuda.empty_cache()
