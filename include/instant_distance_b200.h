@@ -123,6 +123,24 @@ IDB_API void* idb_index_stream(idb_index* index);      /* the cudaStream_t all w
 IDB_API idb_status idb_index_sync(idb_index* index);   /* cudaStreamSynchronize on it */
 IDB_API void idb_index_free(idb_index* index);         /* Drop for Hnsw */
 
+/* ---- Index sharded by PointId range across the GPUs of one box (one process per GPU) ------------------------------
+ * The reference has no distributed path; this is north_star's layout: every rank owns an independent index over its
+ * contiguous range of the input rows, every query is searched on every shard, and ONE ncclAllGather of the per-shard
+ * top-k (packed (distance, global id) keys) is followed by a merge kernel.  Results: the k smallest (distance, global id)
+ * of the union of the shards' `nearest` lists; identical on every rank. */
+#define IDB_UNIQUE_ID_BYTES 128
+typedef struct idb_comm idb_comm;
+IDB_API idb_status idb_comm_unique_id(void* out_unique_id /* IDB_UNIQUE_ID_BYTES, made on one rank, shared by the host app */);
+IDB_API idb_status idb_comm_create(const void* unique_id, int32_t rank, int32_t world, int32_t device, idb_comm** out);
+IDB_API void idb_comm_free(idb_comm* comm);
+/* global_ids[pid] = the caller's id of the row that became PointId pid on this shard (NULL clears the map). */
+IDB_API idb_status idb_index_set_id_map(idb_index* index, const uint32_t* global_ids);
+/* Collective over `comm`: every rank passes the same queries.  out_ids are GLOBAL ids. */
+IDB_API idb_status idb_sharded_search_batch_f32(idb_index* shard, idb_comm* comm, const float* queries, uint64_t nq, uint32_t ef_search,
+                                        uint32_t k, uint32_t* out_ids, float* out_dist, uint32_t* out_len);
+IDB_API idb_status idb_sharded_search_batch_device(idb_index* shard, idb_comm* comm, const float* d_queries, uint64_t nq,
+                                           uint32_t ef_search, uint32_t k, uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len);
+
 /* The canonical squared-L2 of one pair, evaluated on the device (used by parity tests; FloatArray::distance, py:378-421). */
 IDB_API idb_status idb_distance_f32(const float* a, const float* b, uint32_t dim, int32_t device, float* out);
 

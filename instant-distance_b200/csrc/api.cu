@@ -84,6 +84,10 @@ static cudaError_t ensure(T*& p, size_t& cap, size_t need) {
     return e;
 }
 
+cudaError_t ensure_u32(uint32_t*& p, size_t& cap, size_t need) { return ensure(p, cap, need); }
+cudaError_t ensure_u64(uint64_t*& p, size_t& cap, size_t need) { return ensure(p, cap, need); }
+cudaError_t ensure_f32(float*& p, size_t& cap, size_t need) { return ensure(p, cap, need); }
+
 static uint32_t next_pow2(uint64_t v) {
     uint32_t p = 1;
     while (p < v && p < (1u << 30)) p <<= 1;
@@ -166,6 +170,9 @@ idb_status Index::enqueue_search(const float* d_queries_padded, uint64_t nq, uin
     a.gslots = sc.gslots;
     a.gshift = 32 - (uint32_t)std::log2((double)sc.gslots);
     a.tie_tables = sc.tie_tables;
+    a.variant = variant;
+    a.out_keys = pending_out_keys;
+    a.id_map = d_id_map;
 
     const int ch = (int)((nchunks + 31) / 32);
     if (ch > 8) return fail(IDB_ERR_UNSUPPORTED, "dim %u > 1024 is not supported yet", dim);
@@ -229,6 +236,11 @@ Index::~Index() {
     cudaFree(sc.ids);
     cudaFree(sc.dist);
     cudaFree(sc.len);
+    cudaFree(sc.keys_local);
+    cudaFree(sc.keys_all);
+    cudaFree(sc.q2);
+    cudaFree(sc.ids2);
+    cudaFree(d_id_map);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -252,7 +264,8 @@ idb_status Index::init_device(int dev) {
     if (const char* e = std::getenv("IDB_OPT")) opt_flags = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("IDB_VIS_MULT")) vis_mult = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("IDB_L2_PERSIST")) l2_persist = std::atoi(e) != 0;
-    if (const char* e = std::getenv("IDB_CTAS_PER_SM")) ctas_per_sm = std::min(kSearchCtasPerSm, std::max(1, std::atoi(e)));
+    if (const char* e = std::getenv("IDB_CTAS_PER_SM")) ctas_per_sm = std::min(kMaxCtasPerSm, std::max(1, std::atoi(e)));
+    if (const char* e = std::getenv("IDB_VARIANT")) variant = std::atoi(e);
     return IDB_OK;
 }
 

@@ -161,7 +161,7 @@ struct SelectSmem {
 // KA: descent of every insert of the batch (lib.rs:443-463).  Output: `nearest` (ascending keys) per insert.
 // ---------------------------------------------------------------------------------------------------------
 template <int CH, int ROW_T, int EF_T, int B>
-__global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) insert_search_kernel(BuildArgs a) {
+__global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) insert_search_kernel(BuildArgs a) {  // same occupancy as K1
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;

@@ -177,12 +177,32 @@ __device__ __forceinline__ void vis_migrate_to_big(VisitedSet& v, int lane) {
     vis_clear_small(v, lane);
     v.use_big = true;
 }
-// Visited::insert (types.rs:32-40) for one id per lane.  Returns false for lanes with !want.
-// Caller guarantees capacity via vis_reserve.
+// Visited::insert (types.rs:32-40) for one id per lane, split in two so a lane can have the first probes of all its
+// row entries in flight before it waits for any of them:
+//   vis_probe  issues the first CAS and returns (old value, slot);  vis_settle follows the probe chain if needed.
+// Returns false for lanes with !want.  Caller guarantees capacity via vis_reserve.
+struct VisProbe { uint32_t old, h; };
+__device__ __forceinline__ VisProbe vis_probe(VisitedSet& v, uint32_t pid, bool want) {
+    VisProbe r;
+    r.old = 0u;
+    r.h = v.use_big ? (vis_hash(pid) >> v.gshift) : (vis_hash(pid) >> (32 - 9));
+    if (want) r.old = atomicCAS((v.use_big ? v.big : v.small) + r.h, kInvalid, pid);
+    return r;
+}
+__device__ __forceinline__ bool vis_settle(VisitedSet& v, uint32_t pid, bool want, VisProbe r) {
+    if (!want) return false;
+    uint32_t* tab = v.use_big ? v.big : v.small;
+    const uint32_t mask = v.use_big ? v.gslots - 1 : (uint32_t)(kSmallVisSlots - 1);
+    uint32_t old = r.old, h = r.h;
+    for (;;) {
+        if (old == kInvalid) return true;
+        if (old == pid) return false;
+        h = (h + 1) & mask;
+        old = atomicCAS(tab + h, kInvalid, pid);
+    }
+}
 __device__ __forceinline__ bool vis_insert(VisitedSet& v, uint32_t pid, bool want) {
-    bool fresh = false;
-    if (want) fresh = v.use_big ? vis_insert_big(v.big, v.gshift, v.gslots - 1, pid) : vis_insert_small(v.small, pid);
-    return fresh;
+    return vis_settle(v, pid, want, vis_probe(v, pid, want));
 }
 // Make room for `incoming` more ids.  Returns false if the big table would exceed 3/4 load (query is aborted
 // with kQueryVisitedOverflow and retried by the host with a larger table).
@@ -218,39 +238,49 @@ __device__ __forceinline__ uint32_t lower_bound_keys(const uint64_t* a, uint32_t
     return lo;
 }
 
-// Distances from q to the n_new points listed in s.cpid (shared), NB rows in flight per lane; writes the keys
-// (canonical distance bits << 32 | pid) to s.ckey.  The only place in the traversal that touches point rows.
-template <int CH, int NB>
-__device__ __forceinline__ void batch_distances(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid, uint64_t* ckey,
-                                                uint32_t n_new, int lane) {
+// Distances from q to the n_new points listed in cpid (shared, 16-byte aligned), NB rows in flight per lane; writes the
+// keys (canonical distance bits << 32 | pid) to ckey.  The only place in the traversal that touches point rows.
+// kFull: every lane owns a real chunk in every one of its CH slots (dim is a multiple of 128) -> no chunk predicates.
+template <int CH, int NB, bool kFull>
+__device__ __forceinline__ void batch_distances_impl(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid,
+                                                     uint64_t* ckey, uint32_t n_new, int lane) {
+    const uint32_t row_bytes = g.nchunks * 16u;
+    const char* lane_base = reinterpret_cast<const char*>(g.points) + lane * 16;
     if (g.flags & kOptPrefetchVectors) {  // pull every row of this expansion into L2 now; the batches below then hit L2
         const uint32_t lines = (g.nchunks + 7) / 8;  // 128-byte lines per row
-        for (uint32_t t = lane; t < n_new * lines; t += 32) {
-            const uint32_t c = t / lines, ln = t - c * lines;
-            prefetch_l2(g.points + (size_t)cpid[c] * g.nchunks + ln * 8);
-        }
+        for (uint32_t ln = 0; ln < lines; ++ln)
+            for (uint32_t c = lane; c < n_new; c += 32)
+                prefetch_l2(reinterpret_cast<const char*>(g.points) + (size_t)cpid[c] * row_bytes + ln * 128u);
     }
+    bool cok[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) cok[j] = kFull || (uint32_t)(lane + 32 * j) < g.nchunks;
 #pragma unroll 1
     for (uint32_t b0 = 0; b0 < n_new; b0 += NB) {
+        const uint32_t nb = n_new - b0;  // rows in this batch (uniform); entries i >= nb are predicated off
         float4 v[NB][CH];
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            const bool ok = b0 + i < n_new;
-            const uint32_t pid = ok ? cpid[b0 + i] : 0u;  // shared-memory broadcast
-            const float4* row = g.points + (size_t)pid * g.nchunks;
+            // branch-free on purpose: `if (i < nb) {load; use}` makes ptxas emit two branches per row
+            const bool ok = (uint32_t)i < nb;
+            const char* row = lane_base + (size_t)cpid[b0 + i] * row_bytes;  // shared-memory broadcast of the id
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                const uint32_t c = lane + 32 * j;
-                v[i][j] = (ok && c < g.nchunks) ? __ldg(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int j = 0; j < CH; ++j)
+                v[i][j] = (ok && cok[j]) ? __ldg(reinterpret_cast<const float4*>(row + j * 512)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float p[NB];
 #pragma unroll
         for (int i = 0; i < NB; ++i) p[i] = lane_partial<CH>(q, v[i]);
         const float total = batch_butterfly<NB>(p, lane);
-        if (lane < NB && b0 + lane < n_new) ckey[b0 + lane] = mk_key(total, cpid[b0 + lane]);
+        if ((uint32_t)lane < nb && lane < NB) ckey[b0 + lane] = mk_key(total, cpid[b0 + lane]);
     }
     __syncwarp();
+}
+template <int CH, int NB>
+__device__ __forceinline__ void batch_distances(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid, uint64_t* ckey,
+                                                uint32_t n_new, int lane) {
+    // (a second, predicate-free instantiation for dim % 128 == 0 was tried: the two inlined copies made ptxas spill)
+    batch_distances_impl<CH, NB, false>(g, q, cpid, ckey, n_new, lane);
 }
 
 // Rare path: something was evicted while its distance equals the new furthest distance.  Such an entry stays a
@@ -397,9 +427,12 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
 
             // ---- visited.insert for every row entry (lib.rs:705), compacted in row order ------------------
             if (!vis_reserve(s.vis, count, lane)) { s.status = kQueryVisitedOverflow; break; }
+            VisProbe probe[ROW_T];
+#pragma unroll
+            for (int t = 0; t < ROW_T; ++t) probe[t] = vis_probe(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count);
 #pragma unroll
             for (int t = 0; t < ROW_T; ++t) {
-                const bool fresh = vis_insert(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count);
+                const bool fresh = vis_settle(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count, probe[t]);
                 const uint32_t m = __ballot_sync(kFullMask, fresh);
                 if (fresh) s.cpid[n_new + __popc(m & lt_mask)] = ent[t];
                 n_new += __popc(m);

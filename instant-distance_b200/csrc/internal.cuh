@@ -14,6 +14,7 @@ namespace idb {
 
 constexpr int kSearchWarps = 4;        // warps (= live queries) per CTA
 constexpr int kSearchCtasPerSm = 4;    // resident CTAs per SM -> 16 live queries per SM, <= 128 registers per thread
+constexpr int kMaxCtasPerSm = 8;       // upper bound over the tuning variants (scratch is sized for it)
 constexpr int kRetryWarps = 32;        // warps of the (normally idle) overflow-retry pass
 constexpr uint32_t kRetrySlots = 1u << 21;
 
@@ -46,6 +47,9 @@ struct SearchArgs {
     uint32_t* vis_tables;
     uint32_t gslots, gshift;
     uint64_t* tie_tables;
+    uint64_t* out_keys;                // optional: nq x k packed (distance bits << 32 | id_map[pid]) for the sharded all-gather
+    const uint32_t* id_map;            // optional: PointId -> caller's global row id
+    int variant;                       // tuning variant of the kernel template (0 = default)
 };
 
 struct Scratch {
@@ -61,6 +65,11 @@ struct Scratch {
     uint32_t* ids = nullptr;      size_t ids_cap = 0;
     float* dist = nullptr;        size_t dist_cap = 0;
     uint32_t* len = nullptr;      size_t len_cap = 0;
+    // sharded search
+    uint64_t* keys_local = nullptr; size_t keys_local_cap = 0;
+    uint64_t* keys_all = nullptr;   size_t keys_all_cap = 0;
+    float* q2 = nullptr;          size_t q2_cap = 0;
+    uint32_t* ids2 = nullptr;     size_t ids2_cap = 0;
 };
 
 struct Index {
@@ -76,6 +85,8 @@ struct Index {
     std::vector<uint32_t*> d_upper;            // [l-1] -> n_l x M
     std::vector<uint64_t> upper_n;
     const uint32_t** d_upper_ptrs = nullptr;   // device copy of the pointer table
+    uint32_t* d_id_map = nullptr;              // shard: PointId -> global row id (idb_index_set_id_map)
+    uint64_t* pending_out_keys = nullptr;      // set by the sharded path around enqueue_search
 
     Scratch sc;
     uint64_t last_nq = 0;
@@ -84,6 +95,7 @@ struct Index {
     uint32_t vis_mult = 2;        // visited table slots = next_pow2(vis_mult * 2M * ef)
     bool l2_persist = false;      // pin the visited tables in L2 with an access-policy window
     int ctas_per_sm = kSearchCtasPerSm;
+    int variant = 0;              // IDB_VARIANT: alternative (rows in flight, CTAs/SM) instantiations of K1
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t last_launches = 0;
@@ -100,5 +112,8 @@ struct Index {
 };
 
 cudaError_t fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t st);
+cudaError_t ensure_u32(uint32_t*& p, size_t& cap, size_t need);
+cudaError_t ensure_u64(uint64_t*& p, size_t& cap, size_t need);
+cudaError_t ensure_f32(float*& p, size_t& cap, size_t need);
 
 }  // namespace idb

@@ -8,8 +8,8 @@ namespace idb {
 // ---------------------------------------------------------------------------------------------------------
 // K1: batched Hnsw::search — persistent grid, one warp per live query, queries claimed from an atomic counter.
 // ---------------------------------------------------------------------------------------------------------
-template <int CH, int ROW_T, int EF_T, int B>
-__global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) search_kernel(SearchArgs a) {
+template <int CH, int ROW_T, int EF_T, int B, int OCC>
+__global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -56,7 +56,9 @@ __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) search_ke
         const uint32_t len = ok ? s.cnt : 0u;
         for (uint32_t j = lane; j < a.k; j += 32) {
             uint64_t key = j < len ? near[j] : 0ull;
-            a.out_ids[qi * a.k + j] = j < len ? key_pid(key) : kInvalid;
+            const uint32_t gid = j < len ? (a.id_map ? a.id_map[key_pid(key)] : key_pid(key)) : kInvalid;
+            a.out_ids[qi * a.k + j] = gid;
+            if (a.out_keys) a.out_keys[qi * a.k + j] = j < len ? (((uint64_t)key_dbits(key) << 32) | gid) : kKeyNone;
             if (a.out_dist) a.out_dist[qi * a.k + j] = j < len ? __uint_as_float(key_dbits(key)) : __int_as_float(0x7f800000);
         }
         if (lane == 0) {
@@ -71,11 +73,11 @@ __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) search_ke
     }
 }
 
-template <int CH, int ROW_T, int EF_T, int B>
+template <int CH, int ROW_T, int EF_T, int B, int OCC = kSearchCtasPerSm>
 static cudaError_t launch_search(const SearchArgs& a, int grid, cudaStream_t stream) {
     constexpr int kWarpBytes = 2 * 32 * EF_T * 8 + kSmallVisSlots * 4 + 128 * 4 + 128 * 8;
     const int smem = kWarpBytes * kSearchWarps;
-    auto kern = search_kernel<CH, ROW_T, EF_T, B>;
+    auto kern = search_kernel<CH, ROW_T, EF_T, B, OCC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kSearchWarps * 32, smem, stream>>>(a);

@@ -1,0 +1,249 @@
+// sharded.cu — the index sharded by PointId range across the GPUs of one box (BASELINE config 5).
+//
+// One process per GPU.  Every rank owns an independent HNSW over its contiguous range of the input rows (own shuffle, own
+// PointId space, own entry point); every query is searched on every shard with the same ef; then ONE ncclAllGather of the
+// per-shard top-k — packed as u64 keys (canonical distance bits << 32 | global row id) by K1's epilogue — and a merge
+// kernel that keeps the k smallest keys of the union, ties broken by the lower global id.  No other collective anywhere.
+// NCCL is bound at run time (dlopen of libnccl.so.2: the system 2.27 or whichever copy the host application already loaded).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+
+#include "internal.cuh"
+
+namespace idb {
+
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl() {
+    static NcclApi api = [] {
+        NcclApi a;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            a.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (a.handle) break;
+        }
+        if (!a.handle) return a;
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(a.handle, "ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(a.handle, "ncclCommInitRank"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(a.handle, "ncclCommDestroy"));
+        a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(a.handle, "ncclAllGather"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(a.handle, "ncclGetErrorString"));
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+
+#define NCCL_TRY(expr)                                                                                                   \
+    do {                                                                                                                 \
+        ncclResult_t r__ = (expr);                                                                                       \
+        if (r__ != ncclSuccess) return ::idb::fail(IDB_ERR_NCCL, "NCCL error at %s:%d: %s", __FILE__, __LINE__, nccl().GetErrorString(r__)); \
+    } while (0)
+
+// K4: merge of G sorted k-lists per query (one warp per query).  rank(key) = position in its own list + sum over the
+// other lists of lower_bound(list, key); keys are unique (global ids are), so ranks are a permutation.
+__global__ void merge_topk_kernel(const uint64_t* all_keys /* G x nq x k */, uint32_t G, uint64_t nq, uint32_t k,
+                                  uint32_t* out_ids, float* out_dist, uint32_t* out_len) {
+    extern __shared__ uint64_t sm_keys[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    uint64_t* keys = sm_keys + (size_t)warp * G * k;
+    for (uint64_t q = (uint64_t)blockIdx.x * wpb + warp; q < nq; q += (uint64_t)gridDim.x * wpb) {
+        for (uint32_t t = lane; t < G * k; t += 32) {
+            const uint32_t g = t / k, j = t - g * k;
+            keys[t] = all_keys[((size_t)g * nq + q) * k + j];
+        }
+        __syncwarp();
+        uint32_t found = 0;
+        for (uint32_t t = lane; t < G * k; t += 32) {
+            const uint32_t g = t / k, j = t - g * k;
+            const uint64_t key = keys[t];
+            if (key == kKeyNone) continue;
+            uint32_t rank = j;
+            for (uint32_t g2 = 0; g2 < G; ++g2) {
+                if (g2 == g) continue;
+                const uint64_t* l = keys + (size_t)g2 * k;
+                uint32_t lo = 0, hi = k;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (l[mid] < key) lo = mid + 1; else hi = mid;
+                }
+                rank += lo;
+            }
+            if (rank < k) {
+                out_ids[q * k + rank] = (uint32_t)key;
+                if (out_dist) out_dist[q * k + rank] = __uint_as_float((uint32_t)(key >> 32));
+            }
+        }
+        // number of real results = min(k, total non-empty keys); pad the tail
+        uint32_t real = 0;
+        for (uint32_t t = lane; t < G * k; t += 32) real += keys[t] != kKeyNone ? 1u : 0u;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) real += __shfl_xor_sync(kFullMask, real, off);
+        found = min(real, k);
+        for (uint32_t j = found + lane; j < k; j += 32) {
+            out_ids[q * k + j] = kInvalid;
+            if (out_dist) out_dist[q * k + j] = __int_as_float(0x7f800000);
+        }
+        if (out_len && lane == 0) out_len[q] = found;
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1, device = 0;
+};
+
+}  // namespace idb
+
+using namespace idb;
+
+extern "C" {
+
+idb_status idb_comm_unique_id(void* out) {
+    if (!out) return fail(IDB_ERR_INVALID_ARG, "out is null");
+    if (!nccl().ok) return fail(IDB_ERR_NCCL, "libnccl.so.2 could not be loaded (%s)", dlerror() ? dlerror() : "symbols missing");
+    static_assert(IDB_UNIQUE_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "unique id size");
+    ncclUniqueId id;
+    NCCL_TRY(nccl().GetUniqueId(&id));
+    std::memcpy(out, &id, sizeof(id));
+    return IDB_OK;
+}
+
+idb_status idb_comm_create(const void* unique_id, int32_t rank, int32_t world, int32_t device, idb_comm** out) {
+    if (!unique_id || !out) return fail(IDB_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world) return fail(IDB_ERR_INVALID_ARG, "rank %d / world %d invalid", rank, world);
+    if (!nccl().ok) return fail(IDB_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    CUDA_TRY(cudaSetDevice(device));
+    auto* c = new (std::nothrow) Comm();
+    if (!c) return fail(IDB_ERR_OOM, "host allocation failed");
+    c->rank = rank;
+    c->world = world;
+    c->device = device;
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, sizeof(id));
+    ncclResult_t r = nccl().CommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        delete c;
+        return fail(IDB_ERR_NCCL, "ncclCommInitRank failed: %s", nccl().GetErrorString(r));
+    }
+    *out = reinterpret_cast<idb_comm*>(c);
+    return IDB_OK;
+}
+
+void idb_comm_free(idb_comm* comm) {
+    Comm* c = reinterpret_cast<Comm*>(comm);
+    if (!c) return;
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    delete c;
+}
+
+idb_status idb_index_set_id_map(idb_index* index, const uint32_t* global_ids) {
+    if (!index) return fail(IDB_ERR_INVALID_ARG, "index is null");
+    Index* ix = reinterpret_cast<Index*>(index);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CUDA_TRY(cudaSetDevice(ix->device));
+    if (!global_ids) {
+        cudaFree(ix->d_id_map);
+        ix->d_id_map = nullptr;
+        return IDB_OK;
+    }
+    if (ix->n == 0) return IDB_OK;
+    if (!ix->d_id_map) CUDA_TRY(cudaMalloc(&ix->d_id_map, ix->n * 4));
+    CUDA_TRY(cudaMemcpyAsync(ix->d_id_map, global_ids, ix->n * 4, cudaMemcpyHostToDevice, ix->stream));
+    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    return IDB_OK;
+}
+
+// All device pointers; d_queries is nq x dim.  Collective: every rank of `comm` calls it with the same queries.
+idb_status idb_sharded_search_batch_device(idb_index* index, idb_comm* comm, const float* d_queries, uint64_t nq, uint32_t ef_search,
+                                           uint32_t k, uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len) {
+    if (!index || !comm) return fail(IDB_ERR_INVALID_ARG, "index/comm is null");
+    Index* ix = reinterpret_cast<Index*>(index);
+    Comm* c = reinterpret_cast<Comm*>(comm);
+    if (nq == 0) return IDB_OK;
+    if (!d_queries || !d_out_ids || k == 0) return fail(IDB_ERR_INVALID_ARG, "bad argument");
+    if ((uint64_t)c->world * k * 8 > 96 * 1024) return fail(IDB_ERR_UNSUPPORTED, "world * k = %u too large for the merge kernel", c->world * k);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CUDA_TRY(cudaSetDevice(ix->device));
+    const size_t per = (size_t)nq * k;
+    CUDA_TRY(ensure_u64(ix->sc.keys_local, ix->sc.keys_local_cap, per));
+    CUDA_TRY(ensure_u64(ix->sc.keys_all, ix->sc.keys_all_cap, per * c->world));
+    CUDA_TRY(ensure_u32(ix->sc.ids, ix->sc.ids_cap, per));
+    const uint32_t ef = ef_search ? ef_search : ix->ef_search;
+    if (ix->n == 0 || ef == 0) {
+        CUDA_TRY(cudaMemsetAsync(ix->sc.keys_local, 0xFF, per * 8, ix->stream));  // kKeyNone everywhere
+    } else {
+        const float* qp = d_queries;
+        const size_t stride = (size_t)ix->nchunks * 4;
+        if (stride != ix->dim || (reinterpret_cast<uintptr_t>(d_queries) & 15)) {
+            CUDA_TRY(ensure_f32(ix->sc.q, ix->sc.q_cap, nq * stride));
+            CUDA_TRY(cudaMemsetAsync(ix->sc.q, 0, nq * stride * 4, ix->stream));
+            CUDA_TRY(cudaMemcpy2DAsync(ix->sc.q, stride * 4, d_queries, ix->dim * 4, ix->dim * 4, nq, cudaMemcpyDeviceToDevice, ix->stream));
+            qp = ix->sc.q;
+        }
+        ix->pending_out_keys = ix->sc.keys_local;  // K1's epilogue packs (distance bits, global id) keys
+        idb_status st = ix->enqueue_search(qp, nq, ef, k, ix->sc.ids, nullptr, nullptr);
+        ix->pending_out_keys = nullptr;
+        if (st != IDB_OK) return st;
+    }
+    NCCL_TRY(nccl().AllGather(ix->sc.keys_local, ix->sc.keys_all, per, ncclUint64, c->comm, ix->stream));
+    const int wpb = 4;
+    const size_t smem = (size_t)wpb * c->world * k * 8;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::min<uint64_t>((nq + wpb - 1) / wpb, (uint64_t)ix->num_sms * 8);
+    merge_topk_kernel<<<grid, wpb * 32, smem, ix->stream>>>(ix->sc.keys_all, (uint32_t)c->world, nq, k, d_out_ids, d_out_dist, d_out_len);
+    CUDA_TRY(cudaGetLastError());
+    ix->last_launches += 2;  // all-gather + merge
+    return IDB_OK;
+}
+
+idb_status idb_sharded_search_batch_f32(idb_index* index, idb_comm* comm, const float* queries, uint64_t nq, uint32_t ef_search, uint32_t k,
+                                        uint32_t* out_ids, float* out_dist, uint32_t* out_len) {
+    if (!index || !comm) return fail(IDB_ERR_INVALID_ARG, "index/comm is null");
+    Index* ix = reinterpret_cast<Index*>(index);
+    if (nq == 0) return IDB_OK;
+    if (!queries || !out_ids || k == 0) return fail(IDB_ERR_INVALID_ARG, "bad argument");
+    float* dq = nullptr;
+    uint32_t *d_ids = nullptr, *d_len = nullptr;
+    float* d_dist = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ix->mu);
+        CUDA_TRY(cudaSetDevice(ix->device));
+        CUDA_TRY(ensure_f32(ix->sc.q2, ix->sc.q2_cap, nq * ix->dim));
+        CUDA_TRY(ensure_u32(ix->sc.ids2, ix->sc.ids2_cap, nq * k));
+        CUDA_TRY(ensure_f32(ix->sc.dist, ix->sc.dist_cap, nq * k));
+        CUDA_TRY(ensure_u32(ix->sc.len, ix->sc.len_cap, nq));
+        dq = ix->sc.q2; d_ids = ix->sc.ids2; d_dist = ix->sc.dist; d_len = ix->sc.len;
+        CUDA_TRY(cudaMemcpyAsync(dq, queries, nq * ix->dim * 4, cudaMemcpyHostToDevice, ix->stream));
+    }
+    idb_status st = idb_sharded_search_batch_device(index, comm, dq, nq, ef_search, k, d_ids, d_dist, d_len);
+    if (st != IDB_OK) return st;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CUDA_TRY(cudaMemcpyAsync(out_ids, d_ids, nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
+    if (out_dist) CUDA_TRY(cudaMemcpyAsync(out_dist, d_dist, nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
+    if (out_len) CUDA_TRY(cudaMemcpyAsync(out_len, d_len, nq * 4, cudaMemcpyDeviceToHost, ix->stream));
+    uint32_t ctrl[16];
+    if (ix->sc.ctrl) CUDA_TRY(cudaMemcpyAsync(ctrl, ix->sc.ctrl, 64, cudaMemcpyDeviceToHost, ix->stream));
+    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    if (ix->sc.ctrl && ix->n && ctrl[12] != 0)
+        return fail(IDB_ERR_CAPACITY, "%u queries overflowed an internal per-query structure on this shard", ctrl[12]);
+    return IDB_OK;
+}
+
+}  // extern "C"

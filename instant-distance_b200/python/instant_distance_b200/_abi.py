@@ -20,7 +20,8 @@ SYMBOLS = [
     "idb_search_batch_device", "idb_last_search_counters", "idb_index_info", "idb_index_export_points",
     "idb_index_export_zero", "idb_index_export_upper", "idb_index_set_profiling", "idb_index_last_kernel_ms",
     "idb_index_stream", "idb_index_sync", "idb_index_free",
-    "idb_distance_f32", "idb_host_alloc", "idb_host_free", "idb_last_error", "idb_version", "idb_device_count",
+    "idb_comm_unique_id", "idb_comm_create", "idb_comm_free", "idb_index_set_id_map", "idb_sharded_search_batch_f32",
+    "idb_sharded_search_batch_device", "idb_distance_f32", "idb_host_alloc", "idb_host_free", "idb_last_error", "idb_version", "idb_device_count",
 ]
 
 
@@ -76,6 +77,13 @@ def lib():
     L.idb_index_sync.argtypes = [vp]
     L.idb_index_free.argtypes = [vp]
     L.idb_index_free.restype = None
+    L.idb_comm_unique_id.argtypes = [vp]
+    L.idb_comm_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.idb_comm_free.argtypes = [vp]
+    L.idb_comm_free.restype = None
+    L.idb_index_set_id_map.argtypes = [vp, u32p]
+    L.idb_sharded_search_batch_f32.argtypes = [vp, vp, f32p, C.c_uint64, C.c_uint32, C.c_uint32, u32p, f32p, u32p]
+    L.idb_sharded_search_batch_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp]
     L.idb_distance_f32.argtypes = [f32p, f32p, C.c_uint32, C.c_int32, f32p]
     L.idb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.idb_host_free.argtypes = [vp]
@@ -85,7 +93,8 @@ def lib():
     L.idb_device_count.restype = C.c_int32
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("idb_index_stream", "idb_index_free", "idb_host_free", "idb_last_error", "idb_version", "idb_device_count"):
+        if name not in ("idb_index_stream", "idb_index_free", "idb_host_free", "idb_last_error", "idb_version", "idb_device_count",
+                        "idb_comm_free"):
             fn.restype = C.c_int
     _lib = L
     return L
@@ -171,6 +180,23 @@ class Index:
     def search_device(self, d_queries, nq, ef_search, k, d_ids, d_dist, d_len):
         check(lib().idb_search_batch_device(self._h, d_queries, nq, ef_search, k, d_ids, d_dist, d_len))
 
+    def set_id_map(self, global_ids):
+        g = np.ascontiguousarray(global_ids, dtype=np.uint32)
+        check(lib().idb_index_set_id_map(self._h, ptr(g, C.c_uint32)))
+
+    def sharded_search(self, comm, queries, ef_search=0, k=10):
+        q = f32(queries)
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.uint32)
+        dist = np.empty((nq, k), dtype=np.float32)
+        lens = np.empty(nq, dtype=np.uint32)
+        check(lib().idb_sharded_search_batch_f32(self._h, comm._h, ptr(q, C.c_float), nq, ef_search, k, ptr(ids, C.c_uint32),
+                                                 ptr(dist, C.c_float), ptr(lens, C.c_uint32)))
+        return ids, dist, lens
+
+    def sharded_search_device(self, comm, d_queries, nq, ef_search, k, d_ids, d_dist, d_len):
+        check(lib().idb_sharded_search_batch_device(self._h, comm._h, d_queries, nq, ef_search, k, d_ids, d_dist, d_len))
+
     def last_counters(self, nq):
         out = np.zeros((nq, 4), dtype=np.uint64)
         check(lib().idb_last_search_counters(self._h, nq, ptr(out, C.c_uint64)))
@@ -205,6 +231,32 @@ class Index:
 
     def sync(self):
         check(lib().idb_index_sync(self._h))
+
+
+UNIQUE_ID_BYTES = 128
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+    check(lib().idb_comm_unique_id(buf))
+    return bytes(buf.raw)
+
+
+class Comm:
+    """One NCCL communicator (idb_comm): rank `rank` of `world`, bound to CUDA device `device`."""
+
+    def __init__(self, unique_id, rank, world, device):
+        h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, UNIQUE_ID_BYTES)
+        check(lib().idb_comm_create(buf, rank, world, device, C.byref(h)))
+        self._h, self.rank, self.world = h, rank, world
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().idb_comm_free(self._h)
+            self._h = None
+
+    __del__ = close
 
 
 def distance(a, b, device=0):

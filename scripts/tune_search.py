@@ -19,10 +19,10 @@ ap.add_argument("--efc", type=int, default=100)
 ap.add_argument("--M", type=int, default=32)
 ap.add_argument("--seed", type=int, default=20260923)
 ap.add_argument("--data", default="sift")
-ap.add_argument("--graph", default="oracle")
+ap.add_argument("--graph", default="gpu")
 ap.add_argument("--batch", type=int, default=10000)
 ap.add_argument("--steps", type=int, default=5)
-ap.add_argument("--configs", default="0,2,0,4;1,2,0,4;2,2,0,4;3,2,0,4;3,1,0,4;3,2,1,4;3,1,1,4;3,2,0,3;3,2,0,2")
+ap.add_argument("--configs", default="3,2,0,4,0;3,4,0,4,0;3,8,0,4,0;3,4,0,5,1;3,4,0,6,2;3,4,0,8,3;0,4,0,4,0")
 args = ap.parse_args()
 args.no_cache = False
 
@@ -48,8 +48,8 @@ d_len = torch.empty((args.batch,), dtype=torch.int32, device="cuda")
 ref_ids = None
 results = []
 for cfg in args.configs.split(";"):
-    opt, vis, l2p, ctas = cfg.split(",")
-    os.environ.update({"IDB_OPT": opt, "IDB_VIS_MULT": vis, "IDB_L2_PERSIST": l2p, "IDB_CTAS_PER_SM": ctas})
+    opt, vis, l2p, ctas, var = cfg.split(",")
+    os.environ.update({"IDB_OPT": opt, "IDB_VIS_MULT": vis, "IDB_L2_PERSIST": l2p, "IDB_CTAS_PER_SM": ctas, "IDB_VARIANT": var})
     ix = _abi.Index.from_graph(p, zero, upper, args.M, args.ef)
     ix.set_profiling(True)
     ms = []
@@ -63,7 +63,7 @@ for cfg in args.configs.split(";"):
         ref_ids = ids
     same = bool((ids == ref_ids).all())
     byts = float(bench.algorithmic_bytes(ix.last_counters(args.batch), args.dim, args.M, k).sum())
-    r = {"opt": int(opt), "vis_mult": int(vis), "l2_persist": int(l2p), "ctas_per_sm": int(ctas), "kernel_ms": float(np.mean(ms)),
+    r = {"opt": int(opt), "vis_mult": int(vis), "l2_persist": int(l2p), "ctas_per_sm": int(ctas), "variant": int(var), "kernel_ms": float(np.mean(ms)),
          "min_ms": float(np.min(ms)), "GBps": byts / (np.mean(ms) / 1e3) / 1e9, "qps": args.batch / (np.mean(ms) / 1e3), "same_ids": same}
     print(json.dumps(r), flush=True)
     results.append(r)
