@@ -91,8 +91,8 @@ struct Index {
     Scratch sc;
     uint64_t last_nq = 0;
     // tuning knobs (env IDB_OPT / IDB_VIS_MULT / IDB_L2_PERSIST / IDB_CTAS_PER_SM); none of them changes results
-    uint32_t opt_flags = kOptPrefetchVectors | kOptPrefetchRows;
-    uint32_t vis_mult = 2;        // visited table slots = next_pow2(vis_mult * 2M * ef)
+    uint32_t opt_flags = 0;       // L2 prefetch of rows/vectors: measured neutral-to-negative once 16 rows are in flight (profiles/r01_call4)
+    uint32_t vis_mult = 4;        // visited table slots = next_pow2(vis_mult * 2M * ef): load <= ~0.15, probe chains ~1
     bool l2_persist = false;      // pin the visited tables in L2 with an access-policy window
     int ctas_per_sm = kSearchCtasPerSm;
     int variant = 0;              // IDB_VARIANT: alternative (rows in flight, CTAs/SM) instantiations of K1

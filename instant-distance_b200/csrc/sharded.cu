@@ -52,35 +52,27 @@ NcclApi& nccl() {
         if (r__ != ncclSuccess) return ::idb::fail(IDB_ERR_NCCL, "NCCL error at %s:%d: %s", __FILE__, __LINE__, nccl().GetErrorString(r__)); \
     } while (0)
 
-// K4: merge of G sorted k-lists per query (one warp per query).  rank(key) = position in its own list + sum over the
-// other lists of lower_bound(list, key); keys are unique (global ids are), so ranks are a permutation.
+// K4: merge of the G per-shard k-lists of one query (one warp per query): keep the k smallest keys of the union.
+// Keys are unique (global ids are), so rank(key) = #{keys smaller} is a permutation.  The lists are NOT assumed sorted by
+// the full key: a shard orders exact-distance ties by its local PointId, the merged order is by global id.
 __global__ void merge_topk_kernel(const uint64_t* all_keys /* G x nq x k */, uint32_t G, uint64_t nq, uint32_t k,
                                   uint32_t* out_ids, float* out_dist, uint32_t* out_len) {
     extern __shared__ uint64_t sm_keys[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     uint64_t* keys = sm_keys + (size_t)warp * G * k;
+    const uint32_t total = G * k;
     for (uint64_t q = (uint64_t)blockIdx.x * wpb + warp; q < nq; q += (uint64_t)gridDim.x * wpb) {
-        for (uint32_t t = lane; t < G * k; t += 32) {
+        for (uint32_t t = lane; t < total; t += 32) {
             const uint32_t g = t / k, j = t - g * k;
             keys[t] = all_keys[((size_t)g * nq + q) * k + j];
         }
         __syncwarp();
         uint32_t found = 0;
-        for (uint32_t t = lane; t < G * k; t += 32) {
-            const uint32_t g = t / k, j = t - g * k;
+        for (uint32_t t = lane; t < total; t += 32) {
             const uint64_t key = keys[t];
             if (key == kKeyNone) continue;
-            uint32_t rank = j;
-            for (uint32_t g2 = 0; g2 < G; ++g2) {
-                if (g2 == g) continue;
-                const uint64_t* l = keys + (size_t)g2 * k;
-                uint32_t lo = 0, hi = k;
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (l[mid] < key) lo = mid + 1; else hi = mid;
-                }
-                rank += lo;
-            }
+            uint32_t rank = 0;
+            for (uint32_t i = 0; i < total; ++i) rank += keys[i] < key ? 1u : 0u;
             if (rank < k) {
                 out_ids[q * k + rank] = (uint32_t)key;
                 if (out_dist) out_dist[q * k + rank] = __uint_as_float((uint32_t)(key >> 32));
@@ -88,7 +80,7 @@ __global__ void merge_topk_kernel(const uint64_t* all_keys /* G x nq x k */, uin
         }
         // number of real results = min(k, total non-empty keys); pad the tail
         uint32_t real = 0;
-        for (uint32_t t = lane; t < G * k; t += 32) real += keys[t] != kKeyNone ? 1u : 0u;
+        for (uint32_t t = lane; t < total; t += 32) real += keys[t] != kKeyNone ? 1u : 0u;
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) real += __shfl_xor_sync(kFullMask, real, off);
         found = min(real, k);

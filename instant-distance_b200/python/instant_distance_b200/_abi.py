@@ -130,11 +130,15 @@ class Index:
         self._h = handle
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().idb_index_free(self._h)
-            self._h = None
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.idb_index_free(self._h)
+        self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
 
     @classmethod
     def from_graph(cls, points, zero, upper, M, ef_search=100, device=0):
@@ -181,7 +185,13 @@ class Index:
         check(lib().idb_search_batch_device(self._h, d_queries, nq, ef_search, k, d_ids, d_dist, d_len))
 
     def set_id_map(self, global_ids):
+        """global_ids[pid] = caller's id of the row that became PointId pid; None clears the map."""
+        if global_ids is None:
+            check(lib().idb_index_set_id_map(self._h, None))
+            return
         g = np.ascontiguousarray(global_ids, dtype=np.uint32)
+        if g.shape[0] != int(self.info().n):
+            raise ValueError("id map must have one entry per point")
         check(lib().idb_index_set_id_map(self._h, ptr(g, C.c_uint32)))
 
     def sharded_search(self, comm, queries, ef_search=0, k=10):
@@ -252,11 +262,15 @@ class Comm:
         self._h, self.rank, self.world = h, rank, world
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().idb_comm_free(self._h)
-            self._h = None
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.idb_comm_free(self._h)
+        self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
 
 
 def distance(a, b, device=0):

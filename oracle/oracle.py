@@ -130,9 +130,12 @@ class Index:
         self._keep = keepalive
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_free(self._h)
+        try:
+            if getattr(self, "_h", None) and _lib is not None:
+                _lib.orc_free(self._h)
             self._h = None
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
 
     @property
     def n(self):

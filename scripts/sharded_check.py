@@ -22,9 +22,9 @@ from instant_distance_b200 import _abi, sharded  # noqa: E402
 from tests import datagen  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=200_000)
+ap.add_argument("--points", type=int, default=200_000)
 ap.add_argument("--dim", type=int, default=128)
-ap.add_argument("--nq", type=int, default=2000)
+ap.add_argument("--queries", type=int, default=2000)
 ap.add_argument("--k", type=int, default=10)
 ap.add_argument("--ef", type=int, default=100)
 ap.add_argument("--bench", type=int, default=0, help="timed repetitions of the sharded search")
@@ -43,9 +43,9 @@ def exchange(uid):
 
 
 gen = datagen.sift_shaped
-lo, hi = sharded.shard_range(args.n, rank, world)
-rows = gen(args.n, args.dim, 5)[lo:hi]
-q = gen(args.nq, args.dim, 6)
+lo, hi = sharded.shard_range(args.points, rank, world)
+rows = gen(args.points, args.dim, 5)[lo:hi]
+q = gen(args.queries, args.dim, 6)
 t0 = time.time()
 sh = sharded.ShardedIndex(rows, lo, rank, world, local, exchange, seed=100 + rank)
 build_s = time.time() - t0
@@ -73,37 +73,47 @@ local_ids = O2.shuffle(hi - lo, 100 + rank)
 gmap = sharded.global_id_map(local_ids, lo)
 gids = np.where(l_ids == 0xFFFFFFFF, 0, gmap[np.minimum(l_ids, hi - lo - 1)])
 keys = sharded.pack_keys(l_d, gids, np.minimum(l_lens, args.k))
-gathered = [torch.empty((args.nq, args.k), dtype=torch.int64) for _ in range(world)]
+gathered = [torch.empty((args.queries, args.k), dtype=torch.int64) for _ in range(world)]
 dist.all_gather(gathered, torch.from_numpy(keys.view(np.int64)))
 m_ids, m_d, m_lens = sharded.merge_keys(np.stack([g.numpy().view(np.uint64) for g in gathered]), args.k)
 ok_merge = bool((m_ids == ids).all() and m_d.tobytes() == d.tobytes() and (m_lens == lens).all())
+diag = {}
+if not ok_merge:
+    bad = np.nonzero((m_ids != ids).any(axis=1) | (m_lens != lens))[0]
+    diag = {"rank": rank, "bad_rows": int(len(bad)), "dist_bits_equal": bool(m_d.tobytes() == d.tobytes()),
+            "lens_equal": bool((m_lens == lens).all())}
+    if len(bad):
+        b = int(bad[0])
+        diag.update(first=b, fused_ids=ids[b].tolist(), proto_ids=m_ids[b].tolist(), fused_d=d[b].tolist(), proto_d=m_d[b].tolist(),
+                    fused_len=int(lens[b]), proto_len=int(m_lens[b]))
+    print("DIAG", json.dumps(diag), file=sys.stderr, flush=True)
 
 flags = torch.tensor([int(ok_local), int(ok_merge)])
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
-res = {"world": world, "n": args.n, "shard": [lo, hi], "build_s": round(build_s, 2), "local_eq_oracle": bool(flags[0]),
+res = {"world": world, "n": args.points, "shard": [lo, hi], "build_s": round(build_s, 2), "local_eq_oracle": bool(flags[0]),
        "fused_eq_protocol": bool(flags[1])}
 
 if args.bench:
     sh.index.set_id_map(gmap)
     dq = torch.from_numpy(q).cuda()
-    d_ids = torch.empty((args.nq, args.k), dtype=torch.int32, device="cuda")
-    d_d = torch.empty((args.nq, args.k), dtype=torch.float32, device="cuda")
-    d_l = torch.empty((args.nq,), dtype=torch.int32, device="cuda")
+    d_ids = torch.empty((args.queries, args.k), dtype=torch.int32, device="cuda")
+    d_d = torch.empty((args.queries, args.k), dtype=torch.float32, device="cuda")
+    d_l = torch.empty((args.queries,), dtype=torch.int32, device="cuda")
     stream = torch.cuda.ExternalStream(sh.index.stream, device=local)
     for _ in range(3):
-        sh.index.sharded_search_device(sh.comm, dq.data_ptr(), args.nq, args.ef, args.k, d_ids.data_ptr(), d_d.data_ptr(), d_l.data_ptr())
+        sh.index.sharded_search_device(sh.comm, dq.data_ptr(), args.queries, args.ef, args.k, d_ids.data_ptr(), d_d.data_ptr(), d_l.data_ptr())
     sh.index.sync()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.bench):
-        sh.index.sharded_search_device(sh.comm, dq.data_ptr(), args.nq, args.ef, args.k, d_ids.data_ptr(), d_d.data_ptr(), d_l.data_ptr())
+        sh.index.sharded_search_device(sh.comm, dq.data_ptr(), args.queries, args.ef, args.k, d_ids.data_ptr(), d_d.data_ptr(), d_l.data_ptr())
     e1.record(stream)
     e1.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / args.bench])
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     res["sharded_ms_per_batch"] = float(ms)
-    res["sharded_qps"] = args.nq / (float(ms) / 1e3)
+    res["sharded_qps"] = args.queries / (float(ms) / 1e3)
 if rank == 0:
     print(json.dumps(res), flush=True)
 sh.close()

@@ -98,3 +98,14 @@ def test_merge_keys_pads_and_orders():
     assert ids.tolist() == [[3, 7, 2, 9]] and dist.tolist() == [[0.25, 0.5, 1.0, 1.0]] and lens.tolist() == [4]
     ids, dist, lens = sharded.merge_keys(keys, 6)
     assert ids[0].tolist() == [3, 7, 2, 9, 5, 0xFFFFFFFF] and lens.tolist() == [5] and np.isinf(dist[0][5])
+
+
+def test_merge_orders_exact_ties_by_global_id():
+    """A shard orders exact-distance ties by its LOCAL PointId; the merged list is ordered by (distance, global id)."""
+    from instant_distance_b200 import sharded
+
+    d = np.array([[1.0, 2.0, 2.0]], dtype=np.float32)
+    keys = np.stack([sharded.pack_keys(d, np.array([[5, 9, 4]], dtype=np.uint32), [3]),   # tie 9-before-4: local pid order
+                     sharded.pack_keys(d + 10, np.array([[1, 2, 3]], dtype=np.uint32), [3])])
+    ids, dist, lens = sharded.merge_keys(keys, 3)
+    assert ids.tolist() == [[5, 4, 9]] and lens.tolist() == [3]
