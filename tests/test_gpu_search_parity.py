@@ -77,6 +77,14 @@ def test_search_parity_10k_x32_config0(abi, oracle):
     _check(abi, oracle, ix.export(), ix, datagen.uniform(1000, 32, 43), 100, k=10)
 
 
+def test_search_parity_pid_space_beyond_16_bits(abi, oracle):
+    """n > 65535: the b16 visited tables (IDB_VIS_MODE 1/2) split a PointId into (quotient, 16-bit remainder)."""
+    pts = datagen.uniform(150_000, 8, 3)
+    ix, _ = oracle.build(pts, seed=5, threads=8)
+    _check(abi, oracle, ix.export(), ix, datagen.uniform(2000, 8, 4), 100, k=10)
+    _check(abi, oracle, ix.export(), ix, datagen.uniform(500, 8, 5), 128)
+
+
 def test_search_parity_sift_shaped(abi, oracle):
     pts = datagen.sift_shaped(20_000, 128, 1)
     ix, _ = oracle.build(pts, seed=3, threads=8)
