@@ -113,6 +113,12 @@ IDB_API idb_status idb_index_export_points(const idb_index* index, float* out /*
 IDB_API idb_status idb_index_export_zero(const idb_index* index, uint32_t* out /* n x 2M */);
 IDB_API idb_status idb_index_export_upper(const idb_index* index, uint32_t layer /* 1-based */, uint32_t* out /* n_l x M */);
 
+/* Hnsw::dump / Hnsw::load of the Python binding (py:121-137): bincode-1.3 layout of `Hnsw{ef_search, points, zero, layers}`
+ * (core:193-199).  dim and M are not stored in the file (fixed-size arrays in the reference: dim = 300, M = 32), so load takes
+ * them.  *out_values_offset (may be NULL) = file offset where an HnswMap's `values` begin (core:131-134), or the file size. */
+IDB_API idb_status idb_index_save(const idb_index* index, const char* path);
+IDB_API idb_status idb_index_load(const char* path, uint32_t dim, uint32_t M, int32_t device, idb_index** out_index, uint64_t* out_values_offset);
+
 /* Measurement hooks (bench.py): when enabled, CUDA events are recorded on the index stream immediately around the
  * dominant kernel of each call (K1 search_layer for searches); idb_index_last_kernel_ms waits for that kernel and
  * returns its duration and how many of this library's kernels the last call launched. */

@@ -118,11 +118,19 @@ class Hnsw:
         return self._ix.search(q, ef_search=ef_search or self._ef, k=k)
 
     def dump(self, fname):
-        raise NotImplementedError("bincode .idx files are a follow-up (SURVEY §8f-1)")
+        """py:131-137: bincode layout of `Hnsw` (ef_search, points, zero, layers)."""
+        self._ix.save(fname)
 
     @staticmethod
-    def load(fname):
-        raise NotImplementedError("bincode .idx files are a follow-up (SURVEY §8f-1)")
+    def load(fname, dim=300, M=32):
+        """py:121-129.  The file does not store dim / M (fixed arrays in the reference: 300 / 32)."""
+        try:
+            ix, _ = _abi.Index.load(fname, dim, M)
+        except _abi.IdbError as e:
+            if e.status == _abi.ERR_IO:
+                raise OSError(str(e)) from e
+            raise ValueError(f"deserialization error: {e}") from e
+        return Hnsw(ix)
 
 
 class HnswMap(Hnsw):
@@ -141,3 +149,41 @@ class HnswMap(Hnsw):
     @property
     def values(self):
         return self._values
+
+    def dump(self, fname):
+        """py:69-75: `HnswMap { hnsw, values }` — the Hnsw body, then Vec<MapValue::String> (u32 variant 0, u64 len, utf-8)."""
+        import struct
+
+        self._ix.save(fname)
+        with open(fname, "ab") as f:
+            f.write(struct.pack("<Q", len(self._values)))
+            for v in self._values:
+                b = v.encode("utf-8")
+                f.write(struct.pack("<IQ", 0, len(b)) + b)
+
+    @staticmethod
+    def load(fname, dim=300, M=32):
+        """py:58-67."""
+        import struct
+
+        try:
+            ix, off = _abi.Index.load(fname, dim, M)
+        except _abi.IdbError as e:
+            if e.status == _abi.ERR_IO:
+                raise OSError(str(e)) from e
+            raise ValueError(f"deserialization error: {e}") from e
+        values = []
+        with open(fname, "rb") as f:
+            f.seek(off)
+            head = f.read(8)
+            if len(head) != 8:
+                raise ValueError("deserialization error: no values section (an Hnsw file, not an HnswMap?)")
+            (count,) = struct.unpack("<Q", head)
+            for _ in range(count):
+                variant, ln = struct.unpack("<IQ", f.read(12))
+                if variant != 0:
+                    raise ValueError(f"deserialization error: unknown MapValue variant {variant}")
+                values.append(f.read(ln).decode("utf-8"))
+        if len(values) != int(ix.info().n):
+            raise ValueError("deserialization error: values length does not match the point count")
+        return HnswMap(ix, values)

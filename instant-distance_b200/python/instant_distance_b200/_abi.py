@@ -18,7 +18,7 @@ OK, ERR_INVALID_ARG, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_IO, ERR_FORMAT, ERR_CAPACI
 SYMBOLS = [
     "idb_params_default", "idb_build_f32", "idb_index_from_graph_f32", "idb_search_batch_f32",
     "idb_search_batch_device", "idb_last_search_counters", "idb_index_info", "idb_index_export_points",
-    "idb_index_export_zero", "idb_index_export_upper", "idb_index_set_profiling", "idb_index_last_kernel_ms",
+    "idb_index_export_zero", "idb_index_export_upper", "idb_index_save", "idb_index_load", "idb_index_set_profiling", "idb_index_last_kernel_ms",
     "idb_index_stream", "idb_index_sync", "idb_index_free",
     "idb_comm_unique_id", "idb_comm_create", "idb_comm_free", "idb_index_set_id_map", "idb_sharded_search_batch_f32",
     "idb_sharded_search_batch_device", "idb_distance_f32", "idb_host_alloc", "idb_host_free", "idb_last_error", "idb_version", "idb_device_count",
@@ -70,6 +70,8 @@ def lib():
     L.idb_index_export_points.argtypes = [vp, f32p]
     L.idb_index_export_zero.argtypes = [vp, u32p]
     L.idb_index_export_upper.argtypes = [vp, C.c_uint32, u32p]
+    L.idb_index_save.argtypes = [vp, C.c_char_p]
+    L.idb_index_load.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(vp), u64p]
     L.idb_index_set_profiling.argtypes = [vp, C.c_int32]
     L.idb_index_last_kernel_ms.argtypes = [vp, f32p, u32p]
     L.idb_index_stream.argtypes = [vp]
@@ -161,6 +163,16 @@ class Index:
         h = C.c_void_p()
         check(lib().idb_build_f32(ptr(rows, C.c_float), n, dim, C.byref(p), C.byref(h), ptr(ids, C.c_uint32)))
         return cls(h), ids
+
+    def save(self, path):
+        check(lib().idb_index_save(self._h, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path, dim=300, M=32, device=0):
+        """Returns (Index, offset of the HnswMap values in the file)."""
+        h, off = C.c_void_p(), C.c_uint64()
+        check(lib().idb_index_load(os.fsencode(path), dim, M, device, C.byref(h), C.byref(off)))
+        return cls(h), int(off.value)
 
     def info(self):
         i = Info()
