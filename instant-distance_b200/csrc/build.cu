@@ -5,12 +5,13 @@
 //                                                 the rand crate is not vendored in the reference tree: parity unpinned)
 //   3. per layer, top first      lib.rs:304-329  batches of concurrent inserts (KA -> K2 -> sort -> K2'), then the
 //                                                 UpperNode snapshot (K5)
-// The batch schedule replaces rayon: batch = min(max_batch, max(1, inserted / growth)); the top layer is sequential like the
+// The batch schedule replaces rayon: batch = min(16384, max(1, inserted / 8)); the top layer is sequential like the
 // reference's (lib.rs:313-314).  insert_batch = 1 reproduces the sequential reference order exactly.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -208,8 +209,14 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
 
     // ---- batch schedule + scratch -------------------------------------------------------------------------------
     const uint32_t efc = p.ef_construction;
-    const uint32_t max_batch = p.insert_batch ? p.insert_batch : 4096u;
-    const uint32_t growth = 16;  // a batch never exceeds 1/16 of the graph it is inserted into
+    // Defaults from the sweep in profiles/r01_call11/12_tune_build_1M.jsonl (1M x 128): batch <= 16384 and <= 1/8 of the graph
+    // keeps recall@10 within 0.002 of the reference algorithm's own graph (0.9713 vs 0.9729) at 2.5x the speed of batch 4096.
+    uint32_t max_batch = p.insert_batch ? p.insert_batch : 16384u;
+    uint32_t growth = 8;  // a batch never exceeds 1/8 of the graph it is inserted into
+    if (!p.insert_batch) {  // tuning knobs for experiments (results stay valid HNSW graphs; determinism per setting)
+        if (const char* e = std::getenv("IDB_BUILD_MAXBATCH")) max_batch = (uint32_t)std::max(1, std::atoi(e));
+        if (const char* e = std::getenv("IDB_BUILD_GROWTH")) growth = (uint32_t)std::max(1, std::atoi(e));
+    }
     const uint32_t cand_cap = std::max<uint32_t>((efc + 31) / 32 * 32, cap + kNewCap);
     BuildScratch bs;
     CUDA_TRY(cudaMalloc(&bs.cand_keys, (size_t)max_batch * cand_cap * 8));
@@ -226,7 +233,10 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
     if (s0 != IDB_OK) return s0;
 
     const int ch = (int)((ix->nchunks + 31) / 32);
-    const bool stage = SelectSmem::bytes(cand_cap, M, ix->nchunks, true) <= 56 * 1024;
+    // Staging the kept rows in shared memory (72 KB per 2-warp CTA -> 6 warps per SM) measured 1.4x SLOWER than reading them
+    // through L1/L2 with 32 resident warps (profiles/r01_call11_tune_build_1M.jsonl), so it is off unless asked for.
+    bool stage = false;
+    if (const char* e = std::getenv("IDB_BUILD_STAGE")) stage = std::atoi(e) != 0 && SelectSmem::bytes(cand_cap, M, ix->nchunks, true) <= 56 * 1024;
     const uint32_t k2_smem = (uint32_t)SelectSmem::bytes(cand_cap, M, ix->nchunks, stage);
 
     BuildArgs a;

@@ -68,37 +68,42 @@ __device__ __forceinline__ uint32_t select_heuristic_warp(const GraphView& g, co
         }
     }
     uint32_t kept = 0, nd = 0;
+    bool cok[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) cok[j] = (uint32_t)(lane + 32 * j) < g.nchunks;
+    const uint32_t row_bytes = g.nchunks * 16u;
+    const char* gbase = reinterpret_cast<const char*>(g.points) + lane * 16;
+    const char* sbase = reinterpret_cast<const char*>(kept_vecs) + lane * 16;
     for (uint32_t i = 0; i < W; ++i) {
         if (kept >= cap) break;  // lib.rs:669
         const uint64_t ck = cand[i];
         const uint32_t cpid = key_pid(ck), cbits = key_dbits(ck);
         float4 q[CH];
-        const float4* qrow = g.points + (size_t)cpid * g.nchunks;
+        const char* qrow = gbase + (size_t)cpid * row_bytes;
 #pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            const uint32_t c = lane + 32 * j;
-            q[j] = c < g.nchunks ? __ldg(qrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int j = 0; j < CH; ++j)
+            q[j] = cok[j] ? __ldg(reinterpret_cast<const float4*>(qrow + j * 512)) : make_float4(0.f, 0.f, 0.f, 0.f);
         bool closer = false;
 #pragma unroll 1
         for (uint32_t b0 = 0; b0 < kept && !closer; b0 += NB) {
+            const uint32_t nb = kept - b0;  // uniform
             float4 v[NB][CH];
 #pragma unroll
             for (int r = 0; r < NB; ++r) {
-                const bool ok = b0 + r < kept;
-                const float4* row = kStage ? kept_vecs + (size_t)(b0 + r) * g.nchunks
-                                           : g.points + (size_t)(ok ? kept_pid[b0 + r] : 0u) * g.nchunks;
+                const bool ok = (uint32_t)r < nb;  // branch-free: predicated loads, see batch_distances
+                const char* row = kStage ? sbase + (size_t)(b0 + r) * row_bytes
+                                         : gbase + (size_t)(ok ? kept_pid[b0 + r] : 0u) * row_bytes;
 #pragma unroll
                 for (int j = 0; j < CH; ++j) {
-                    const uint32_t c = lane + 32 * j;
-                    v[r][j] = (ok && c < g.nchunks) ? (kStage ? row[c] : __ldg(row + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4* pr = reinterpret_cast<const float4*>(row + j * 512);
+                    v[r][j] = (ok && cok[j]) ? (kStage ? *pr : __ldg(pr)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             float p[NB];
 #pragma unroll
             for (int r = 0; r < NB; ++r) p[r] = lane_partial<CH>(q, v[r]);
             const float total = batch_butterfly<NB>(p, lane);
-            const bool hit = lane < NB && b0 + lane < kept && canon_bits(total) < cbits;
+            const bool hit = (uint32_t)lane < nb && lane < NB && canon_bits(total) < cbits;
             closer = __any_sync(kFullMask, hit);
         }
         if (!closer) {
