@@ -296,6 +296,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    if world > 1:
+        args.no_cache = True  # every rank builds its own replica on its own GPU; no shared cache file
     pts, gen = make_workload(args)
     p, zero, upper, how = obtain_graph(args, pts, local_rank)
     ix = _abi.Index.from_graph(p, zero, upper, args.M, args.ef, device=local_rank)
@@ -409,7 +411,7 @@ def main():
 
     # ---- CPU baseline (rank 0, N=1 leg only) + parity spot check against it --------------------------------------
     cpu = None
-    if rank == 0 and not args.skip_cpu_baseline:
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:  # reported at N=1 only
         from oracle import oracle as O
 
         T = host_threads()
