@@ -277,7 +277,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=10_000)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 0)
+    args.warmup = max(args.warmup, 3)  # timing rule: at least 3 untimed warm-up steps
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
