@@ -26,6 +26,8 @@ extern "C" {
 #endif
 
 #define IDB_INVALID 0xFFFFFFFFu
+#define IDB_STORAGE_F32 0u
+#define IDB_STORAGE_BF16 1u
 
 #if defined(__GNUC__)
 #define IDB_API __attribute__((visibility("default")))
@@ -62,6 +64,8 @@ typedef struct idb_params {
     uint32_t insert_batch;      /* GPU build: concurrent inserts per step (rayon's worker count in the
                                    reference, core:316-318).  0 = auto, 1 = strictly sequential order. */
     int32_t  device;            /* CUDA device ordinal */
+    uint32_t storage;           /* IDB_STORAGE_F32 (default) or IDB_STORAGE_BF16: rows rounded to bf16 (RNE) and kept in HBM at
+                                   half the bytes; distances still accumulate in fp32 in the same canonical order */
 } idb_params;
 
 /* Builder::default() (core:101-113) — except `seed`, which the reference draws from entropy; here 0. */
@@ -80,6 +84,12 @@ IDB_API idb_status idb_build_f32(const float* rows, uint64_t n, uint32_t dim, co
 IDB_API idb_status idb_index_from_graph_f32(const float* points, uint64_t n, uint32_t dim, uint32_t M, uint32_t ef_search,
                                     const uint32_t* zero, uint32_t n_upper, const uint32_t* const* upper,
                                     const uint64_t* upper_n, int32_t device, idb_index** out_index);
+
+/* Same, but the point rows are rounded to bf16 and stored that way (BASELINE config 4's data format).  Results equal the f32
+ * engine / the reference algorithm run on the bf16-rounded points. */
+IDB_API idb_status idb_index_from_graph_bf16(const float* points, uint64_t n, uint32_t dim, uint32_t M, uint32_t ef_search,
+                                     const uint32_t* zero, uint32_t n_upper, const uint32_t* const* upper,
+                                     const uint64_t* upper_n, int32_t device, idb_index** out_index);
 
 /* Hnsw::search(point, &mut Search) (core:352-383), batched: one independent search per query row.
  * The reference returns the whole `nearest` list (<= ef_search items, ascending by (distance, pid));
@@ -107,6 +117,7 @@ typedef struct idb_info {
     uint32_t n_layers;          /* 0 for an empty index, else 1 + number of upper layers */
     uint64_t layer_n[32];       /* node count per layer, [0] = n */
     int32_t  device;
+    uint32_t storage;           /* IDB_STORAGE_* */
 } idb_info;
 IDB_API idb_status idb_index_info(const idb_index* index, idb_info* out);
 IDB_API idb_status idb_index_export_points(const idb_index* index, float* out /* n x dim */);

@@ -59,6 +59,21 @@ __global__ void distance_kernel(const float4* a, const float4* b, uint32_t nchun
     if (lane == 0) *out = s;
 }
 
+// f32 -> bf16 (round to nearest even) and back (exact), element-wise over the padded row matrix
+__global__ void narrow_bf16_kernel(const float* src, uint16_t* dst, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t b = __float_as_uint(src[i]);
+        uint32_t r;
+        if ((b & 0x7fffffffu) > 0x7f800000u) r = (b >> 16) | 0x40u;           // NaN stays NaN
+        else r = (b + 0x7fffu + ((b >> 16) & 1u)) >> 16;                       // RNE
+        dst[i] = (uint16_t)r;
+    }
+}
+__global__ void widen_bf16_kernel(const uint16_t* src, float* dst, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = __uint_as_float((uint32_t)src[i] << 16);
+}
+
 __global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -205,9 +220,41 @@ idb_status Index::enqueue_search(const float* d_queries_padded, uint64_t nq, uin
     return IDB_OK;
 }
 
+idb_status Index::narrow_points_to_bf16() {
+    const size_t total = n * (size_t)nchunks * 4;
+    if (total == 0) { bf16 = true; return IDB_OK; }
+    CUDA_TRY(cudaMalloc(&d_points_bf16, total * 2));
+    narrow_bf16_kernel<<<num_sms * 8, 256, 0, stream>>>(d_points, d_points_bf16, total);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    cudaFree(d_points);
+    d_points = nullptr;
+    bf16 = true;
+    return IDB_OK;
+}
+
+idb_status Index::copy_points_f32(float* host_out, uint64_t r0, uint64_t m) {
+    if (m == 0) return IDB_OK;
+    const size_t stride = (size_t)nchunks * 4;
+    if (!bf16) {
+        CUDA_TRY(cudaMemcpy2DAsync(host_out, dim * 4, d_points + r0 * stride, stride * 4, dim * 4, m, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        return IDB_OK;
+    }
+    float* tmp = nullptr;
+    CUDA_TRY(cudaMalloc(&tmp, m * stride * 4));
+    widen_bf16_kernel<<<num_sms * 8, 256, 0, stream>>>(d_points_bf16 + r0 * stride, tmp, m * stride);
+    cudaError_t e = cudaMemcpy2DAsync(host_out, dim * 4, tmp, stride * 4, dim * 4, m, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(tmp);
+    CUDA_TRY(e);
+    return IDB_OK;
+}
+
 GraphView Index::view() const {
     GraphView g;
-    g.points = reinterpret_cast<const float4*>(d_points);
+    g.points = bf16 ? reinterpret_cast<const char*>(d_points_bf16) : reinterpret_cast<const char*>(d_points);
+    g.bf16 = bf16 ? 1u : 0u;
     g.nchunks = nchunks;
     g.zero = d_zero;
     g.upper = d_upper_ptrs;
@@ -222,6 +269,7 @@ Index::~Index() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     cudaFree(d_points);
+    cudaFree(d_points_bf16);
     cudaFree(d_zero);
     for (auto* p : d_upper) cudaFree(p);
     cudaFree(d_upper_ptrs);
@@ -336,12 +384,13 @@ idb_status idb_params_default(idb_params* p) {
     p->keep_pruned = 1;                      // core:125
     p->insert_batch = 0;
     p->device = 0;
+    p->storage = IDB_STORAGE_F32;
     return IDB_OK;
 }
 
-idb_status idb_index_from_graph_f32(const float* points, uint64_t n, uint32_t dim, uint32_t M, uint32_t ef_search,
-                                    const uint32_t* zero, uint32_t n_upper, const uint32_t* const* upper,
-                                    const uint64_t* upper_n, int32_t device, idb_index** out_index) {
+static idb_status index_from_graph(const float* points, uint64_t n, uint32_t dim, uint32_t M, uint32_t ef_search,
+                                   const uint32_t* zero, uint32_t n_upper, const uint32_t* const* upper,
+                                   const uint64_t* upper_n, int32_t device, bool bf16, idb_index** out_index) {
     if (!out_index) return fail(IDB_ERR_INVALID_ARG, "out_index is null");
     *out_index = nullptr;
     if (dim == 0) return fail(IDB_ERR_INVALID_ARG, "dim must be >= 1");
@@ -354,9 +403,22 @@ idb_status idb_index_from_graph_f32(const float* points, uint64_t n, uint32_t di
     if (!ix) return fail(IDB_ERR_OOM, "host allocation failed");
     idb_status st = ix->init_device(device);
     if (st == IDB_OK) st = ix->upload(points, n, dim, M, ef_search, zero, n_upper, upper, upper_n);
+    if (st == IDB_OK && bf16) st = ix->narrow_points_to_bf16();
     if (st != IDB_OK) { delete ix; return st; }
     *out_index = reinterpret_cast<idb_index*>(ix);
     return IDB_OK;
+}
+
+idb_status idb_index_from_graph_f32(const float* points, uint64_t n, uint32_t dim, uint32_t M, uint32_t ef_search,
+                                    const uint32_t* zero, uint32_t n_upper, const uint32_t* const* upper,
+                                    const uint64_t* upper_n, int32_t device, idb_index** out_index) {
+    return index_from_graph(points, n, dim, M, ef_search, zero, n_upper, upper, upper_n, device, false, out_index);
+}
+
+idb_status idb_index_from_graph_bf16(const float* points, uint64_t n, uint32_t dim, uint32_t M, uint32_t ef_search,
+                                     const uint32_t* zero, uint32_t n_upper, const uint32_t* const* upper,
+                                     const uint64_t* upper_n, int32_t device, idb_index** out_index) {
+    return index_from_graph(points, n, dim, M, ef_search, zero, n_upper, upper, upper_n, device, true, out_index);
 }
 
 idb_status idb_search_batch_device(idb_index* index, const float* d_queries, uint64_t nq, uint32_t ef_search, uint32_t k,
@@ -452,6 +514,7 @@ idb_status idb_index_info(const idb_index* index, idb_info* out) {
     out->M = ix->M;
     out->ef_search = ix->ef_search;
     out->device = ix->device;
+    out->storage = ix->bf16 ? IDB_STORAGE_BF16 : IDB_STORAGE_F32;
     out->n_layers = ix->n == 0 ? 0 : (uint32_t)ix->d_upper.size() + 1;
     if (ix->n) out->layer_n[0] = ix->n;
     for (size_t l = 0; l < ix->upper_n.size() && l + 1 < 32; ++l) out->layer_n[l + 1] = ix->upper_n[l];
@@ -464,9 +527,8 @@ idb_status idb_index_export_points(const idb_index* index, float* out) {
     if (ix->n == 0) return IDB_OK;
     std::lock_guard<std::mutex> lk(ix->mu);
     CUDA_TRY(cudaSetDevice(ix->device));
-    const size_t stride = (size_t)ix->nchunks * 4;
-    CUDA_TRY(cudaMemcpy2DAsync(out, ix->dim * 4, ix->d_points, stride * 4, ix->dim * 4, ix->n, cudaMemcpyDeviceToHost, ix->stream));
-    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    idb_status st = ix->copy_points_f32(out, 0, ix->n);
+    if (st != IDB_OK) return st;
     return IDB_OK;
 }
 

@@ -193,6 +193,10 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
         cudaFree(d_rows);
         cudaFree(d_order);
     }
+    if (p.storage == IDB_STORAGE_BF16) {
+        idb_status sb = ix->narrow_points_to_bf16();
+        if (sb != IDB_OK) return sb;
+    }
     CUDA_TRY(cudaMalloc(&ix->d_zero, n * (size_t)cap * 4));
     CUDA_TRY(fill_u32(ix->d_zero, n * (size_t)cap, kInvalid, st));
     std::vector<const uint32_t*> ptrs;
@@ -335,6 +339,7 @@ extern "C" idb_status idb_build_f32(const float* rows, uint64_t n, uint32_t dim,
         return fail(IDB_ERR_UNSUPPORTED, "ef_construction = %u unsupported (1..512)", params->ef_construction);
     if (dim > 1024) return fail(IDB_ERR_UNSUPPORTED, "dim %u > 1024 is not supported yet", dim);
     if (!(params->ml > 0.0f) || params->ml >= 1.0f) return fail(IDB_ERR_INVALID_ARG, "ml must be in (0, 1)");
+    if (params->storage != IDB_STORAGE_F32 && params->storage != IDB_STORAGE_BF16) return fail(IDB_ERR_INVALID_ARG, "unknown storage %u", params->storage);
     if (params->heuristic && params->extend_candidates)
         return fail(IDB_ERR_UNSUPPORTED,
                     "Heuristic::extend_candidates = true is not supported: in the reference it re-locks the row being inserted "

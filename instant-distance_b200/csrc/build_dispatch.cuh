@@ -14,27 +14,27 @@ struct BuildLaunch {
     uint32_t smem_per_warp; // K2
 };
 
-template <int CH, int ROW_T, int EF_T, int B>
+template <int CH, int ROW_T, int EF_T, int B, class RT>
 cudaError_t launch_insert_search(const BuildArgs& a, int grid, cudaStream_t st) {
     constexpr int kWarpBytes = 2 * 32 * EF_T * 8 + kSmallVisSlots * 4 + 128 * 4 + 128 * 8;
     const int smem = kWarpBytes * kSearchWarps;
-    auto kern = insert_search_kernel<CH, ROW_T, EF_T, B>;
+    auto kern = insert_search_kernel<CH, ROW_T, EF_T, B, RT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kSearchWarps * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
-template <int CH, int NB, bool kStage>
+template <int CH, int NB, bool kStage, class RT>
 cudaError_t launch_k2(const BuildArgs& a, const BuildLaunch& l, cudaStream_t st) {
     const int smem = (int)l.smem_per_warp * kBuildWarps;
     if (l.op == kOpSelectNew) {
-        auto kern = select_new_kernel<CH, NB, kStage>;
+        auto kern = select_new_kernel<CH, NB, kStage, RT>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         kern<<<l.grid, kBuildWarps * 32, smem, st>>>(a, l.smem_per_warp);
     } else {
-        auto kern = relink_kernel<CH, NB, kStage>;
+        auto kern = relink_kernel<CH, NB, kStage, RT>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         kern<<<l.grid, kBuildWarps * 32, smem, st>>>(a, l.smem_per_warp);
@@ -42,24 +42,29 @@ cudaError_t launch_k2(const BuildArgs& a, const BuildLaunch& l, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int CH, int B, int NB>
-cudaError_t build_dispatch(const BuildArgs& a, const BuildLaunch& l, cudaStream_t st) {
+template <int CH, int B, int NB, class RT>
+cudaError_t build_dispatch_rt(const BuildArgs& a, const BuildLaunch& l, cudaStream_t st) {
     switch (l.op) {
         case kOpInsertSearch:
             if (l.row_t <= 2) {
-                if (l.ef_t <= 4) return launch_insert_search<CH, 2, 4, B>(a, l.grid, st);
-                return launch_insert_search<CH, 2, 16, B>(a, l.grid, st);
+                if (l.ef_t <= 4) return launch_insert_search<CH, 2, 4, B, RT>(a, l.grid, st);
+                return launch_insert_search<CH, 2, 16, B, RT>(a, l.grid, st);
             }
-            if (l.ef_t <= 4) return launch_insert_search<CH, 4, 4, B>(a, l.grid, st);
-            return launch_insert_search<CH, 4, 16, B>(a, l.grid, st);
+            if (l.ef_t <= 4) return launch_insert_search<CH, 4, 4, B, RT>(a, l.grid, st);
+            return launch_insert_search<CH, 4, 16, B, RT>(a, l.grid, st);
         case kOpSelectNew:
         case kOpRelink:
-            return l.stage ? launch_k2<CH, NB, true>(a, l, st) : launch_k2<CH, NB, false>(a, l, st);
+            return l.stage ? launch_k2<CH, NB, true, RT>(a, l, st) : launch_k2<CH, NB, false, RT>(a, l, st);
         case kOpRelinkSimple:
-            relink_simple_kernel<CH><<<l.grid, kBuildWarps * 32, 0, st>>>(a);
+            relink_simple_kernel<CH, RT><<<l.grid, kBuildWarps * 32, 0, st>>>(a);
             return cudaGetLastError();
     }
     return cudaErrorInvalidValue;
+}
+template <int CH, int B, int NB>
+cudaError_t build_dispatch(const BuildArgs& a, const BuildLaunch& l, cudaStream_t st) {
+    if (a.g.bf16) return build_dispatch_rt<CH, B, NB, RowBF16>(a, l, st);
+    return build_dispatch_rt<CH, B, NB, RowF32>(a, l, st);
 }
 
 }  // namespace idb

@@ -54,25 +54,24 @@ struct BuildArgs {
 // Kept rows are staged in shared memory (kStage) so each is fetched from HBM/L2 once; the candidate's own row is the
 // register-resident "query" of the canonical distance.
 // ---------------------------------------------------------------------------------------------------------
-template <int CH, int NB, bool kStage>
+template <int CH, int NB, bool kStage, class RT>
 __device__ __forceinline__ uint32_t select_heuristic_warp(const GraphView& g, const uint64_t* cand, uint32_t W, uint32_t* out,
                                                           uint32_t* disc, float4* kept_vecs, uint32_t* kept_pid,
                                                           bool keep_pruned, int lane) {
     const uint32_t cap = 2 * g.M;
     // warm L2 with every candidate row (each is read once as a "query", kept ones again when not staged)
     {
-        const uint32_t lines = (g.nchunks + 7) / 8;
-        for (uint32_t t = lane; t < W * lines; t += 32) {
-            const uint32_t c = t / lines, ln = t - c * lines;
-            prefetch_l2(g.points + (size_t)key_pid(cand[c]) * g.nchunks + ln * 8);
-        }
+        const uint32_t rb = g.nchunks * RT::kChunkBytes, lines = (rb + 127) / 128;
+        for (uint32_t ln = 0; ln < lines; ++ln)
+            for (uint32_t c = lane; c < W; c += 32) prefetch_l2(g.points + (size_t)key_pid(cand[c]) * rb + ln * 128u);
     }
     uint32_t kept = 0, nd = 0;
     bool cok[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) cok[j] = (uint32_t)(lane + 32 * j) < g.nchunks;
-    const uint32_t row_bytes = g.nchunks * 16u;
-    const char* gbase = reinterpret_cast<const char*>(g.points) + lane * 16;
+    const uint32_t row_bytes = g.nchunks * RT::kChunkBytes;   // global rows (f32 or bf16)
+    const uint32_t srow_bytes = g.nchunks * 16u;               // staged rows are always widened float4
+    const char* gbase = g.points + lane * RT::kChunkBytes;
     const char* sbase = reinterpret_cast<const char*>(kept_vecs) + lane * 16;
     for (uint32_t i = 0; i < W; ++i) {
         if (kept >= cap) break;  // lib.rs:669
@@ -81,8 +80,7 @@ __device__ __forceinline__ uint32_t select_heuristic_warp(const GraphView& g, co
         float4 q[CH];
         const char* qrow = gbase + (size_t)cpid * row_bytes;
 #pragma unroll
-        for (int j = 0; j < CH; ++j)
-            q[j] = cok[j] ? __ldg(reinterpret_cast<const float4*>(qrow + j * 512)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < CH; ++j) q[j] = cok[j] ? RT::ld(qrow + j * 32 * RT::kChunkBytes) : make_float4(0.f, 0.f, 0.f, 0.f);
         bool closer = false;
 #pragma unroll 1
         for (uint32_t b0 = 0; b0 < kept && !closer; b0 += NB) {
@@ -91,13 +89,12 @@ __device__ __forceinline__ uint32_t select_heuristic_warp(const GraphView& g, co
 #pragma unroll
             for (int r = 0; r < NB; ++r) {
                 const bool ok = (uint32_t)r < nb;  // branch-free: predicated loads, see batch_distances
-                const char* row = kStage ? sbase + (size_t)(b0 + r) * row_bytes
+                const char* row = kStage ? sbase + (size_t)(b0 + r) * srow_bytes
                                          : gbase + (size_t)(ok ? kept_pid[b0 + r] : 0u) * row_bytes;
 #pragma unroll
-                for (int j = 0; j < CH; ++j) {
-                    const float4* pr = reinterpret_cast<const float4*>(row + j * 512);
-                    v[r][j] = (ok && cok[j]) ? (kStage ? *pr : __ldg(pr)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                for (int j = 0; j < CH; ++j)
+                    v[r][j] = (ok && cok[j]) ? (kStage ? *reinterpret_cast<const float4*>(row + j * 512) : RT::ld(row + j * 32 * RT::kChunkBytes))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             float p[NB];
 #pragma unroll
@@ -165,7 +162,7 @@ struct SelectSmem {
 // ---------------------------------------------------------------------------------------------------------
 // KA: descent of every insert of the batch (lib.rs:443-463).  Output: `nearest` (ascending keys) per insert.
 // ---------------------------------------------------------------------------------------------------------
-template <int CH, int ROW_T, int EF_T, int B>
+template <int CH, int ROW_T, int EF_T, int B, class RT>
 __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) insert_search_kernel(BuildArgs a) {  // same occupancy as K1
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -196,13 +193,8 @@ __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) insert_se
         if (w >= a.count) break;
         const uint32_t neu = a.base + (uint32_t)w;
         float4 q[CH];
-        const float4* qrow = a.g.points + (size_t)neu * a.g.nchunks;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            const uint32_t c = lane + 32 * j;
-            q[j] = c < a.g.nchunks ? __ldg(qrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        descend<CH, ROW_T, EF_T, B, false>(a.g, s, q, a.layer, a.efc, lane, nullptr);
+        load_row<CH, RT>(a.g, neu, lane, q);
+        descend<CH, ROW_T, EF_T, B, false, RT>(a.g, s, q, a.layer, a.efc, lane, nullptr);
         const uint64_t* near = s.near_base + s.cur * s.near_len;
         const uint32_t len = s.status == kQueryOk ? s.cnt : 0u;
         for (uint32_t j = lane; j < len; j += 32) a.cand_keys[(size_t)w * a.cand_cap + j] = near[j] & kKeyMask;
@@ -218,7 +210,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) insert_se
 // ---------------------------------------------------------------------------------------------------------
 // K2: select_heuristic for the new nodes (lib.rs:465-473), own-row write (lib.rs:516) and link-request emission.
 // ---------------------------------------------------------------------------------------------------------
-template <int CH, int NB, bool kStage>
+template <int CH, int NB, bool kStage, class RT>
 __global__ void __launch_bounds__(kBuildWarps * 32) select_new_kernel(BuildArgs a, uint32_t smem_per_warp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -231,8 +223,8 @@ __global__ void __launch_bounds__(kBuildWarps * 32) select_new_kernel(BuildArgs 
         const uint32_t W = a.cand_cnt[w];
         for (uint32_t j = lane; j < W; j += 32) sm.cand[j] = a.cand_keys[(size_t)w * a.cand_cap + j];
         __syncwarp();
-        const uint32_t total = select_heuristic_warp<CH, NB, kStage>(a.g, sm.cand, W, sm.out, sm.disc, sm.kept_vecs, sm.kept_pid,
-                                                                     a.keep_pruned != 0, lane);
+        const uint32_t total = select_heuristic_warp<CH, NB, kStage, RT>(a.g, sm.cand, W, sm.out, sm.disc, sm.kept_vecs, sm.kept_pid,
+                                                                         a.keep_pruned != 0, lane);
         uint32_t* row = a.zero + (size_t)neu * cap;
         for (uint32_t t = lane; t < cap; t += 32) {
             const uint32_t pid = t < total ? sm.out[t] : kInvalid;
@@ -248,7 +240,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32) select_new_kernel(BuildArgs 
 //   candidates = {new...} U row(p), distances w.r.t. points[p]; `push` admission with ef = ef_construction and
 //   no truncation (lib.rs:704-720); then select_heuristic; then the row is rewritten.
 // ---------------------------------------------------------------------------------------------------------
-template <int CH, int NB, bool kStage>
+template <int CH, int NB, bool kStage, class RT>
 __global__ void __launch_bounds__(kBuildWarps * 32) relink_kernel(BuildArgs a, uint32_t smem_per_warp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -266,12 +258,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32) relink_kernel(BuildArgs a, u
         const uint32_t p = (uint32_t)(a.sorted_pairs[pos] >> 32);
         uint32_t* row = a.zero + (size_t)p * cap;
         float4 q[CH];
-        const float4* qrow = a.g.points + (size_t)p * a.g.nchunks;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            const uint32_t c = lane + 32 * j;
-            q[j] = c < a.g.nchunks ? __ldg(qrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        load_row<CH, RT>(a.g, p, lane, q);
         for (;;) {  // rounds of at most kNewCap link requests (one round unless p is a hub of this batch)
             // ---- gather: new ids first (push(new), lib.rs:626), then the row's valid prefix (lib.rs:627-629) ----
             uint32_t n_newc = 0;
@@ -289,7 +276,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32) relink_kernel(BuildArgs a, u
             }
             const uint32_t C = n_newc + rcount;
             __syncwarp();
-            batch_distances<CH, NB>(a.g, q, sm.cpid, sm.ckey, C, lane);
+            batch_distances<CH, NB, RT>(a.g, q, sm.cpid, sm.ckey, C, lane);
             // ---- push admission (lib.rs:704-720, `nearest` is never truncated here): entry j, in push order, enters
             // iff fewer than ef earlier-pushed entries are smaller (counting earlier REJECTED entries is harmless: a
             // rejected entry already has >= ef smaller admitted ones).  Then sort the admitted keys by counting.
@@ -323,8 +310,8 @@ __global__ void __launch_bounds__(kBuildWarps * 32) relink_kernel(BuildArgs a, u
                 }
             }
             __syncwarp();
-            const uint32_t total = select_heuristic_warp<CH, NB, kStage>(a.g, sm.cand, W, sm.out, sm.disc, sm.kept_vecs,
-                                                                         sm.kept_pid, a.keep_pruned != 0, lane);
+            const uint32_t total = select_heuristic_warp<CH, NB, kStage, RT>(a.g, sm.cand, W, sm.out, sm.disc, sm.kept_vecs,
+                                                                             sm.kept_pid, a.keep_pruned != 0, lane);
             for (uint32_t t = lane; t < cap; t += 32) __stcg(row + t, t < total ? sm.out[t] : kInvalid);  // rewrite
             __threadfence();
             __syncwarp();
@@ -334,7 +321,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32) relink_kernel(BuildArgs a, u
 
 // Simple mode reverse link (lib.rs:497-515, incl. the reversed comparator at lib.rs:510) for one (target, new) pair
 // per warp, executed in ascending `new` order for every target (a target's requests are serialised by its warp).
-template <int CH>
+template <int CH, class RT>
 __global__ void __launch_bounds__(kBuildWarps * 32) relink_simple_kernel(BuildArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t cap = 2 * a.g.M;
@@ -348,21 +335,11 @@ __global__ void __launch_bounds__(kBuildWarps * 32) relink_simple_kernel(BuildAr
         const uint32_t p = (uint32_t)(a.sorted_pairs[pos] >> 32);
         uint32_t* row = a.zero + (size_t)p * cap;
         float4 q[CH];
-        const float4* qrow = a.g.points + (size_t)p * a.g.nchunks;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            const uint32_t c = lane + 32 * j;
-            q[j] = c < a.g.nchunks ? __ldg(qrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        load_row<CH, RT>(a.g, p, lane, q);
         auto dist_to = [&](uint32_t pid) -> uint32_t {  // canonical distance bits from points[p] to points[pid]
-            float4 v[1][CH];
-            const float4* r = a.g.points + (size_t)pid * a.g.nchunks;
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                const uint32_t c = lane + 32 * j;
-                v[0][j] = c < a.g.nchunks ? __ldg(r + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            return canon_bits(butterfly_sum(lane_partial<CH>(q, v[0])));
+            float4 v[CH];
+            load_row<CH, RT>(a.g, pid, lane, v);
+            return canon_bits(butterfly_sum(lane_partial<CH>(q, v)));
         };
         while (pos < a.n_pairs_cap && (uint32_t)(a.sorted_pairs[pos] >> 32) == p) {
             const uint32_t neu = (uint32_t)a.sorted_pairs[pos++];

@@ -36,14 +36,15 @@ enum OptFlags : uint32_t { kOptPrefetchVectors = 1u, kOptPrefetchRows = 2u };
 enum QueryStatus : uint32_t { kQueryOk = 0, kQueryVisitedOverflow = 1, kQueryTieOverflow = 2 };
 
 struct GraphView {
-    const float4* points;        // n x nchunks float4 (row stride = dim rounded up to 4 floats, zero padded)
-    uint32_t nchunks;            // float4 chunks per row
+    const char* points;          // n rows of nchunks 4-element chunks (dim rounded up to 4, zero padded); f32 (16 B/chunk) or bf16 (8 B/chunk)
+    uint32_t nchunks;            // 4-element chunks per row
     const uint32_t* zero;        // n x 2M
     const uint32_t* const* upper;  // device array: upper[l-1] = n_l x M
     uint32_t n_upper;
     uint32_t M;
     uint64_t n;
     uint32_t flags;              // kOpt* tuning switches (never change results)
+    uint32_t bf16;               // rows are stored as bf16 (BASELINE config 4's data format); arithmetic stays fp32
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -64,6 +65,29 @@ __device__ __forceinline__ float lane_partial(const float4 (&q)[CH], const float
         a3 = __fmaf_rn(d3, d3, a3);
     }
     return __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+}
+
+// Row storage types.  A lane always owns the same 4 ELEMENTS per 128-element block (chunk l, l+32, ...), so the canonical
+// fp32 summation order is the same for both; bf16 rows are widened exactly (bf16 -> f32 is a 16-bit shift).
+struct RowF32 {
+    static constexpr uint32_t kChunkBytes = 16;
+    static __device__ __forceinline__ float4 ld(const char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+};
+struct RowBF16 {
+    static constexpr uint32_t kChunkBytes = 8;
+    static __device__ __forceinline__ float4 ld(const char* p) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+        return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                           __uint_as_float(u.y & 0xFFFF0000u));
+    }
+};
+// This lane's CH chunks of row `pid` (zeros beyond the row's last chunk).
+template <int CH, class RT>
+__device__ __forceinline__ void load_row(const GraphView& g, uint32_t pid, int lane, float4 (&q)[CH]) {
+    const char* row = g.points + (size_t)pid * (g.nchunks * RT::kChunkBytes) + lane * RT::kChunkBytes;
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+        q[j] = (uint32_t)(lane + 32 * j) < g.nchunks ? RT::ld(row + j * 32 * RT::kChunkBytes) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // Butterfly for ONE vector (offsets 1, 2, 4, 8, 16 — the canonical order): every lane ends with the total.
@@ -241,16 +265,16 @@ __device__ __forceinline__ uint32_t lower_bound_keys(const uint64_t* a, uint32_t
 // Distances from q to the n_new points listed in cpid (shared, 16-byte aligned), NB rows in flight per lane; writes the
 // keys (canonical distance bits << 32 | pid) to ckey.  The only place in the traversal that touches point rows.
 // kFull: every lane owns a real chunk in every one of its CH slots (dim is a multiple of 128) -> no chunk predicates.
-template <int CH, int NB, bool kFull>
+template <int CH, int NB, bool kFull, class RT>
 __device__ __forceinline__ void batch_distances_impl(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid,
                                                      uint64_t* ckey, uint32_t n_new, int lane) {
-    const uint32_t row_bytes = g.nchunks * 16u;
-    const char* lane_base = reinterpret_cast<const char*>(g.points) + lane * 16;
+    const uint32_t row_bytes = g.nchunks * RT::kChunkBytes;
+    const char* lane_base = g.points + lane * RT::kChunkBytes;
     if (g.flags & kOptPrefetchVectors) {  // pull every row of this expansion into L2 now; the batches below then hit L2
-        const uint32_t lines = (g.nchunks + 7) / 8;  // 128-byte lines per row
+        const uint32_t lines = (row_bytes + 127) / 128;  // 128-byte lines per row
         for (uint32_t ln = 0; ln < lines; ++ln)
             for (uint32_t c = lane; c < n_new; c += 32)
-                prefetch_l2(reinterpret_cast<const char*>(g.points) + (size_t)cpid[c] * row_bytes + ln * 128u);
+                prefetch_l2(g.points + (size_t)cpid[c] * row_bytes + ln * 128u);
     }
     bool cok[CH];
 #pragma unroll
@@ -266,7 +290,7 @@ __device__ __forceinline__ void batch_distances_impl(const GraphView& g, const f
             const char* row = lane_base + (size_t)cpid[b0 + i] * row_bytes;  // shared-memory broadcast of the id
 #pragma unroll
             for (int j = 0; j < CH; ++j)
-                v[i][j] = (ok && cok[j]) ? __ldg(reinterpret_cast<const float4*>(row + j * 512)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[i][j] = (ok && cok[j]) ? RT::ld(row + j * 32 * RT::kChunkBytes) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float p[NB];
 #pragma unroll
@@ -276,11 +300,11 @@ __device__ __forceinline__ void batch_distances_impl(const GraphView& g, const f
     }
     __syncwarp();
 }
-template <int CH, int NB>
+template <int CH, int NB, class RT = RowF32>
 __device__ __forceinline__ void batch_distances(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid, uint64_t* ckey,
                                                 uint32_t n_new, int lane) {
     // (a second, predicate-free instantiation for dim % 128 == 0 was tried: the two inlined copies made ptxas spill)
-    batch_distances_impl<CH, NB, false>(g, q, cpid, ckey, n_new, lane);
+    batch_distances_impl<CH, NB, false, RT>(g, q, cpid, ckey, n_new, lane);
 }
 
 // Rare path: something was evicted while its distance equals the new furthest distance.  Such an entry stays a
@@ -366,7 +390,7 @@ __device__ __forceinline__ uint64_t pop_min_tie(WarpState& s, int lane) {
 // kLive: rows may be rewritten concurrently (GPU build) -> read them through L2 (ld.global.cg), not the
 // read-only/L1 path.
 // ---------------------------------------------------------------------------------------------------------
-template <int CH, int ROW_T, int EF_T, int B, bool kLive>
+template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT>
 __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, const float4 (&q)[CH], const uint32_t* rows,
                                              uint32_t width, uint32_t links, uint32_t ef_cur, bool seed_entry, int lane) {
     const uint32_t lt_mask = (1u << lane) - 1;
@@ -444,7 +468,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
         }
 
         // ---- distances (lib.rs:709-710) --------------------------------------------------------------------
-        batch_distances<CH, B>(g, q, s.cpid, s.ckey, n_new, lane);
+        batch_distances<CH, B, RT>(g, q, s.cpid, s.ckey, n_new, lane);
         uint64_t keyg[ROW_T];
 #pragma unroll
         for (int gi = 0; gi < ROW_T; ++gi) {
@@ -565,7 +589,7 @@ __device__ __forceinline__ void cull(WarpState& s, int lane, bool next_big) {
 // Construction::insert's descent (lib.rs:443-463) when target_layer = the insert layer, ef_target = ef_construction.
 // Layers above the target are searched on the UpperNode snapshots with ef = 1; the target layer on the zero table.
 // On return nearest = (s.near_base + s.cur * s.near_len)[0..s.cnt).  counters (if non-null): {n_expand_upper, n_dist_upper, n_expand_target, n_dist_target}.
-template <int CH, int ROW_T, int EF_T, int B, bool kLive>
+template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT = RowF32>
 __device__ __forceinline__ void descend(const GraphView& g, WarpState& s, const float4 (&q)[CH], uint32_t target_layer,
                                         uint32_t ef_target, int lane, uint32_t* counters4) {
     s.cur = 0;
@@ -584,7 +608,7 @@ __device__ __forceinline__ void descend(const GraphView& g, WarpState& s, const 
         const uint32_t* rows = above ? g.upper[cur - 1] : g.zero;
         const uint32_t width = above ? g.M : 2 * g.M;
         const uint32_t links = (above || target_layer != 0) ? g.M : 2 * g.M;  // lib.rs:445 / 366-369
-        search_layer<CH, ROW_T, EF_T, B, kLive>(g, s, q, rows, width, links, above ? 1u : ef_target, seed, lane);
+        search_layer<CH, ROW_T, EF_T, B, kLive, RT>(g, s, q, rows, width, links, above ? 1u : ef_target, seed, lane);
         seed = false;
         if (!above || s.status != kQueryOk) break;
         cull<EF_T>(s, lane, /*next_big=*/(cur - 1 == target_layer));

@@ -80,7 +80,9 @@ struct Index {
 
     uint64_t n = 0;
     uint32_t dim = 0, nchunks = 0, M = 32, ef_search = 100;
-    float* d_points = nullptr;                 // n x nchunks*4 f32 (PointId order)
+    float* d_points = nullptr;                 // n x nchunks*4 f32 (PointId order); null when the rows are stored as bf16
+    uint16_t* d_points_bf16 = nullptr;         // n x nchunks*4 bf16 (storage = IDB_STORAGE_BF16)
+    bool bf16 = false;
     uint32_t* d_zero = nullptr;                // n x 2M
     std::vector<uint32_t*> d_upper;            // [l-1] -> n_l x M
     std::vector<uint64_t> upper_n;
@@ -105,6 +107,8 @@ struct Index {
     idb_status upload(const float* points, uint64_t n, uint32_t dim, uint32_t M, uint32_t ef, const uint32_t* zero,
                       uint32_t n_upper, const uint32_t* const* upper, const uint64_t* upper_n);
     GraphView view() const;
+    idb_status narrow_points_to_bf16();                                  // d_points (f32) -> d_points_bf16, frees d_points
+    idb_status copy_points_f32(float* host_out, uint64_t r0, uint64_t m);  // rows [r0, r0+m) as n x dim f32 on the host
     int search_grid() const;
     idb_status ensure_search_scratch(uint32_t ef, uint64_t nq, uint32_t k);
     idb_status enqueue_search(const float* d_queries_padded, uint64_t nq, uint32_t ef, uint32_t k, uint32_t* d_ids, float* d_dist,

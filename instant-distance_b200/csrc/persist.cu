@@ -35,14 +35,14 @@ idb_status idb_index_save(const idb_index* index, const char* path) {
     out.f = std::fopen(path, "wb");
     if (!out.f) return fail(IDB_ERR_IO, "cannot open %s for writing", path);
     const uint64_t n = ix->n;
-    const size_t stride = (size_t)ix->nchunks * 4;
     bool ok = put_u64(out.f, ix->ef_search) && put_u64(out.f, n);
     // points: n x [f32; dim]
     const uint64_t chunk = 1 << 16;
     std::vector<float> buf((size_t)chunk * ix->dim);
     for (uint64_t r0 = 0; ok && r0 < n; r0 += chunk) {
         const uint64_t m = std::min(chunk, n - r0);
-        CUDA_TRY(cudaMemcpy2D(buf.data(), ix->dim * 4, ix->d_points + r0 * stride, stride * 4, ix->dim * 4, m, cudaMemcpyDeviceToHost));
+        idb_status st = ix->copy_points_f32(buf.data(), r0, m);  // bf16-stored rows are written widened (exact)
+        if (st != IDB_OK) return st;
         ok = put(out.f, buf.data(), m * ix->dim * 4);
     }
     // zero: n x [u32; 2M]

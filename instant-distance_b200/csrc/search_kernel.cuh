@@ -8,7 +8,7 @@ namespace idb {
 // ---------------------------------------------------------------------------------------------------------
 // K1: batched Hnsw::search — persistent grid, one warp per live query, queries claimed from an atomic counter.
 // ---------------------------------------------------------------------------------------------------------
-template <int CH, int ROW_T, int EF_T, int B, int OCC>
+template <int CH, int ROW_T, int EF_T, int B, int OCC, class RT = RowF32>
 __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchAr
             q[j] = c < a.g.nchunks ? __ldg(qrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 
-        descend<CH, ROW_T, EF_T, B, false>(a.g, s, q, 0u, a.ef, lane, a.counters ? a.counters + qi * 4 : nullptr);
+        descend<CH, ROW_T, EF_T, B, false, RT>(a.g, s, q, 0u, a.ef, lane, a.counters ? a.counters + qi * 4 : nullptr);
 
         const bool ok = s.status == kQueryOk;
         const uint64_t* near = (s.near_base + s.cur * s.near_len);
@@ -73,26 +73,30 @@ __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchAr
     }
 }
 
-template <int CH, int ROW_T, int EF_T, int B, int OCC = kSearchCtasPerSm>
+template <int CH, int ROW_T, int EF_T, int B, int OCC = kSearchCtasPerSm, class RT = RowF32>
 static cudaError_t launch_search(const SearchArgs& a, int grid, cudaStream_t stream) {
     constexpr int kWarpBytes = 2 * 32 * EF_T * 8 + kSmallVisSlots * 4 + 128 * 4 + 128 * 8;
     const int smem = kWarpBytes * kSearchWarps;
-    auto kern = search_kernel<CH, ROW_T, EF_T, B, OCC>;
+    auto kern = search_kernel<CH, ROW_T, EF_T, B, OCC, RT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kSearchWarps * 32, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
+template <int CH, int B, class RT>
+cudaError_t dispatch_row_ef_rt(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st) {
+    if (row_t <= 2) {
+        if (ef_t <= 4) return launch_search<CH, 2, 4, B, kSearchCtasPerSm, RT>(a, grid, st);
+        return launch_search<CH, 2, 16, B, kSearchCtasPerSm, RT>(a, grid, st);
+    }
+    if (ef_t <= 4) return launch_search<CH, 4, 4, B, kSearchCtasPerSm, RT>(a, grid, st);
+    return launch_search<CH, 4, 16, B, kSearchCtasPerSm, RT>(a, grid, st);
+}
 template <int CH, int B>
 cudaError_t dispatch_row_ef(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st) {
-    if (row_t <= 2) {
-        if (ef_t <= 4) return launch_search<CH, 2, 4, B>(a, grid, st);
-        return launch_search<CH, 2, 16, B>(a, grid, st);
-    }
-    if (ef_t <= 4) return launch_search<CH, 4, 4, B>(a, grid, st);
-    return launch_search<CH, 4, 16, B>(a, grid, st);
+    if (a.g.bf16) return dispatch_row_ef_rt<CH, B, RowBF16>(a, row_t, ef_t, grid, st);
+    return dispatch_row_ef_rt<CH, B, RowF32>(a, row_t, ef_t, grid, st);
 }
-
 
 }  // namespace idb

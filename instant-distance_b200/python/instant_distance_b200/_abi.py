@@ -16,7 +16,7 @@ INVALID = 0xFFFFFFFF
 OK, ERR_INVALID_ARG, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_IO, ERR_FORMAT, ERR_CAPACITY, ERR_UNSUPPORTED = range(9)
 
 SYMBOLS = [
-    "idb_params_default", "idb_build_f32", "idb_index_from_graph_f32", "idb_search_batch_f32",
+    "idb_params_default", "idb_build_f32", "idb_index_from_graph_f32", "idb_index_from_graph_bf16", "idb_search_batch_f32",
     "idb_search_batch_device", "idb_last_search_counters", "idb_index_info", "idb_index_export_points",
     "idb_index_export_zero", "idb_index_export_upper", "idb_index_save", "idb_index_load", "idb_index_set_profiling", "idb_index_last_kernel_ms",
     "idb_index_stream", "idb_index_sync", "idb_index_free",
@@ -29,14 +29,14 @@ class Params(C.Structure):
     _fields_ = [
         ("M", C.c_uint32), ("ef_construction", C.c_uint32), ("ef_search", C.c_uint32), ("ml", C.c_float),
         ("seed", C.c_uint64), ("heuristic", C.c_int32), ("extend_candidates", C.c_int32), ("keep_pruned", C.c_int32),
-        ("insert_batch", C.c_uint32), ("device", C.c_int32),
+        ("insert_batch", C.c_uint32), ("device", C.c_int32), ("storage", C.c_uint32),
     ]
 
 
 class Info(C.Structure):
     _fields_ = [
         ("n", C.c_uint64), ("dim", C.c_uint32), ("M", C.c_uint32), ("ef_search", C.c_uint32), ("n_layers", C.c_uint32),
-        ("layer_n", C.c_uint64 * 32), ("device", C.c_int32),
+        ("layer_n", C.c_uint64 * 32), ("device", C.c_int32), ("storage", C.c_uint32),
     ]
 
 
@@ -63,6 +63,7 @@ def lib():
     L.idb_build_f32.argtypes = [f32p, C.c_uint64, C.c_uint32, C.POINTER(Params), C.POINTER(vp), u32p]
     L.idb_index_from_graph_f32.argtypes = [f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u32p, C.c_uint32,
                                            C.POINTER(u32p), u64p, C.c_int32, C.POINTER(vp)]
+    L.idb_index_from_graph_bf16.argtypes = L.idb_index_from_graph_f32.argtypes
     L.idb_search_batch_f32.argtypes = [vp, f32p, C.c_uint64, C.c_uint32, C.c_uint32, u32p, f32p, u32p]
     L.idb_search_batch_device.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp]
     L.idb_last_search_counters.argtypes = [vp, C.c_uint64, u64p]
@@ -115,9 +116,14 @@ def ptr(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
+STORAGE = {"f32": 0, "bf16": 1}
+
+
 def default_params(**kw):
     p = Params()
     check(lib().idb_params_default(C.byref(p)))
+    if isinstance(kw.get("storage"), str):
+        kw["storage"] = STORAGE[kw["storage"]]
     if "M" in kw and "ml" not in kw:
         kw["ml"] = float(np.float32(1.0) / np.log(np.float32(kw["M"])))
     for k, v in kw.items():
@@ -143,14 +149,15 @@ class Index:
             pass
 
     @classmethod
-    def from_graph(cls, points, zero, upper, M, ef_search=100, device=0):
+    def from_graph(cls, points, zero, upper, M, ef_search=100, device=0, storage="f32"):
         points, zero = f32(points), np.ascontiguousarray(zero, dtype=np.uint32)
         n, dim = points.shape
         ups = [np.ascontiguousarray(u, dtype=np.uint32) for u in upper]
         arr = (C.POINTER(C.c_uint32) * max(1, len(ups)))(*[ptr(u, C.c_uint32) for u in ups])
         un = np.array([u.shape[0] for u in ups] or [0], dtype=np.uint64)
         h = C.c_void_p()
-        check(lib().idb_index_from_graph_f32(ptr(points, C.c_float), n, dim, M, ef_search, ptr(zero, C.c_uint32), len(ups),
+        fn = lib().idb_index_from_graph_bf16 if storage == "bf16" else lib().idb_index_from_graph_f32
+        check(fn(ptr(points, C.c_float), n, dim, M, ef_search, ptr(zero, C.c_uint32), len(ups),
                                              arr, ptr(un, C.c_uint64), device, C.byref(h)))
         return cls(h)
 
