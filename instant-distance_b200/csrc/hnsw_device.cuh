@@ -69,17 +69,26 @@ __device__ __forceinline__ float lane_partial(const float4 (&q)[CH], const float
 
 // Row storage types.  A lane always owns the same 4 ELEMENTS per 128-element block (chunk l, l+32, ...), so the canonical
 // fp32 summation order is the same for both; bf16 rows are widened exactly (bf16 -> f32 is a 16-bit shift).
+// `Raw` is what a lane keeps in registers while a batch of row loads is in flight (bf16 rows stay packed: half the
+// registers per row, so twice as many rows in flight); widen() runs at the point of use.
 struct RowF32 {
     static constexpr uint32_t kChunkBytes = 16;
-    static __device__ __forceinline__ float4 ld(const char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+    using Raw = float4;
+    static __device__ __forceinline__ Raw ld_raw(const char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+    static __device__ __forceinline__ Raw zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    static __device__ __forceinline__ float4 widen(Raw r) { return r; }
+    static __device__ __forceinline__ float4 ld(const char* p) { return ld_raw(p); }
 };
 struct RowBF16 {
     static constexpr uint32_t kChunkBytes = 8;
-    static __device__ __forceinline__ float4 ld(const char* p) {
-        const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    using Raw = uint2;
+    static __device__ __forceinline__ Raw ld_raw(const char* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+    static __device__ __forceinline__ Raw zero() { return make_uint2(0u, 0u); }
+    static __device__ __forceinline__ float4 widen(Raw u) {
         return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
                            __uint_as_float(u.y & 0xFFFF0000u));
     }
+    static __device__ __forceinline__ float4 ld(const char* p) { return widen(ld_raw(p)); }
 };
 // This lane's CH chunks of row `pid` (zeros beyond the row's last chunk).
 template <int CH, class RT>
@@ -88,6 +97,14 @@ __device__ __forceinline__ void load_row(const GraphView& g, uint32_t pid, int l
 #pragma unroll
     for (int j = 0; j < CH; ++j)
         q[j] = (uint32_t)(lane + 32 * j) < g.nchunks ? RT::ld(row + j * 32 * RT::kChunkBytes) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <int CH, class RT>
+__device__ __forceinline__ float lane_partial_raw(const float4 (&q)[CH], const typename RT::Raw (&r)[CH]) {
+    float4 v[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = RT::widen(r[j]);
+    return lane_partial<CH>(q, v);
 }
 
 // Butterfly for ONE vector (offsets 1, 2, 4, 8, 16 — the canonical order): every lane ends with the total.
@@ -282,7 +299,7 @@ __device__ __forceinline__ void batch_distances_impl(const GraphView& g, const f
 #pragma unroll 1
     for (uint32_t b0 = 0; b0 < n_new; b0 += NB) {
         const uint32_t nb = n_new - b0;  // rows in this batch (uniform); entries i >= nb are predicated off
-        float4 v[NB][CH];
+        typename RT::Raw v[NB][CH];
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
             // branch-free on purpose: `if (i < nb) {load; use}` makes ptxas emit two branches per row
@@ -290,11 +307,11 @@ __device__ __forceinline__ void batch_distances_impl(const GraphView& g, const f
             const char* row = lane_base + (size_t)cpid[b0 + i] * row_bytes;  // shared-memory broadcast of the id
 #pragma unroll
             for (int j = 0; j < CH; ++j)
-                v[i][j] = (ok && cok[j]) ? RT::ld(row + j * 32 * RT::kChunkBytes) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[i][j] = (ok && cok[j]) ? RT::ld_raw(row + j * 32 * RT::kChunkBytes) : RT::zero();
         }
         float p[NB];
 #pragma unroll
-        for (int i = 0; i < NB; ++i) p[i] = lane_partial<CH>(q, v[i]);
+        for (int i = 0; i < NB; ++i) p[i] = lane_partial_raw<CH, RT>(q, v[i]);
         const float total = batch_butterfly<NB>(p, lane);
         if ((uint32_t)lane < nb && lane < NB) ckey[b0 + lane] = mk_key(total, cpid[b0 + lane]);
     }

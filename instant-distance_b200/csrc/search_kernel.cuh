@@ -95,7 +95,8 @@ cudaError_t dispatch_row_ef_rt(const SearchArgs& a, int row_t, int ef_t, int gri
 }
 template <int CH, int B>
 cudaError_t dispatch_row_ef(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st) {
-    if (a.g.bf16) return dispatch_row_ef_rt<CH, B, RowBF16>(a, row_t, ef_t, grid, st);
+    // bf16 rows stay packed while in flight (half the registers per row): twice the rows in flight per lane
+    if (a.g.bf16) return dispatch_row_ef_rt<CH, (2 * B <= 16 ? 2 * B : B), RowBF16>(a, row_t, ef_t, grid, st);
     return dispatch_row_ef_rt<CH, B, RowF32>(a, row_t, ef_t, grid, st);
 }
 

@@ -23,10 +23,10 @@ ap.add_argument("--which", default="config0,uniform,config2")
 args = ap.parse_args()
 
 
-def run(name, gen, n, dim, M, efc, efs, nq, steps=5):
+def run(name, gen, n, dim, M, efc, efs, nq, steps=5, storage="f32"):
     pts = gen(n, dim, 1)
     t0 = time.time()
-    ix, ids = _abi.Index.build(pts, M=M, ef_construction=efc, ef_search=efs[0], seed=7)
+    ix, ids = _abi.Index.build(pts, M=M, ef_construction=efc, ef_search=efs[0], seed=7, storage=storage)
     ix.sync()
     build_s = time.time() - t0
     p, zero, upper = ix.export_graph()
@@ -34,7 +34,8 @@ def run(name, gen, n, dim, M, efc, efs, nq, steps=5):
     truth = bench.brute_force_topk_torch(torch.from_numpy(p).cuda(), rq, 10)
     torch.cuda.empty_cache()
     ix.set_profiling(True)
-    out = {"config": name, "n": n, "dim": dim, "M": M, "ef_construction": efc, "build_s": round(build_s, 2),
+    del pts
+    out = {"config": name, "storage": storage, "n": n, "dim": dim, "M": M, "ef_construction": efc, "build_s": round(build_s, 2),
            "build_points_per_s": n / build_s, "searches": []}
     qs = [torch.from_numpy(gen(nq, dim, 7000 + s)).cuda() for s in range(steps + 2)]
     d_ids = torch.empty((nq, 10), dtype=torch.int32, device="cuda")
@@ -49,7 +50,7 @@ def run(name, gen, n, dim, M, efc, efs, nq, steps=5):
             t, _ = ix.last_kernel_ms()
             if s >= 2:
                 ms.append(t)
-        byts = float(bench.algorithmic_bytes(ix.last_counters(nq), dim, M, 10).sum())
+        byts = float(bench.algorithmic_bytes(ix.last_counters(nq), dim if storage == "f32" else dim // 2, M, 10).sum())
         cnt = ix.last_counters(nq).mean(0).tolist()
         out["searches"].append({"ef_search": ef, "recall_at_10": rec, "kernel_ms": float(np.mean(ms)), "qps": nq / (np.mean(ms) / 1e3),
                                 "GBps": byts / (np.mean(ms) / 1e3) / 1e9, "frac_of_6572": byts / (np.mean(ms) / 1e3) / 1e9 / 6572.5,
@@ -68,5 +69,9 @@ for w in args.which.split(","):
         run("uniform", datagen.uniform, 1_000_000, 128, 32, 100, [100, 200, 300, 400, 512], 10_000)
     elif w == "config2":
         run("config2 2M x 300 M=24 efc=200", datagen.uniform, 2_000_000, 300, 24, 200, [100, 200], 10_000)
+    elif w == "config4":
+        run("config4 5M x 768 bf16 ef=128 batch 64k", datagen.sift_shaped, 5_000_000, 768, 32, 100, [128], 65_536, steps=3, storage="bf16")
+    elif w == "config4s":
+        run("config4 (1M subset) 1M x 768 bf16 ef=128 batch 64k", datagen.sift_shaped, 1_000_000, 768, 32, 100, [128], 65_536, steps=3, storage="bf16")
     elif w == "config2s":
         run("config2 (sift-shaped) 2M x 300 M=24 efc=200", datagen.sift_shaped, 2_000_000, 300, 24, 200, [100, 200], 10_000)
