@@ -74,6 +74,15 @@ __global__ void widen_bf16_kernel(const uint16_t* src, float* dst, size_t n) {
         dst[i] = __uint_as_float((uint32_t)src[i] << 16);
 }
 
+// Adjacency sanity check for graphs adopted from outside (idb_index_from_graph_*, idb_index_load): every entry must be
+// INVALID or a PointId below `limit`; otherwise the traversal would read out of bounds.
+__global__ void validate_rows_kernel(const uint32_t* rows, size_t count, uint32_t limit, uint32_t* bad) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t v = rows[i];
+        if (v != kInvalid && v >= limit) atomicAdd(bad, 1u);
+    }
+}
+
 __global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -350,6 +359,22 @@ idb_status Index::upload(const float* points, uint64_t n_, uint32_t dim_, uint32
     CUDA_TRY(cudaMalloc(&d_upper_ptrs, std::max<size_t>(1, n_upper) * sizeof(uint32_t*)));
     if (n_upper)
         CUDA_TRY(cudaMemcpyAsync(d_upper_ptrs, ptrs.data(), n_upper * sizeof(uint32_t*), cudaMemcpyHostToDevice, stream));
+    // reject graphs whose adjacency points outside the layer it belongs to
+    if (zero) {
+        uint32_t* d_bad = nullptr;
+        CUDA_TRY(cudaMalloc(&d_bad, 4));
+        CUDA_TRY(cudaMemsetAsync(d_bad, 0, 4, stream));
+        validate_rows_kernel<<<num_sms * 4, 256, 0, stream>>>(d_zero, n * 2 * (size_t)M, (uint32_t)n, d_bad);
+        for (uint32_t l = 0; l < n_upper; ++l)
+            if (upper && upper[l] && upper_n_[l])
+                validate_rows_kernel<<<num_sms * 4, 256, 0, stream>>>(d_upper[l], upper_n_[l] * (size_t)M, (uint32_t)upper_n_[l], d_bad);
+        uint32_t bad = 0;
+        cudaError_t e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        cudaFree(d_bad);
+        CUDA_TRY(e);
+        if (bad) return fail(IDB_ERR_INVALID_ARG, "%u adjacency entries refer to PointIds outside their layer", bad);
+    }
     CUDA_TRY(cudaStreamSynchronize(stream));
     return IDB_OK;
 }
