@@ -163,3 +163,19 @@ def test_large_batch_and_roundtrip_export(abi, oracle):
     assert (np.diff(dist, axis=1) >= 0).all()
     ids_b, dist_b, _ = gpu.search(q, ef_search=100, k=10)
     assert (ids_b == ids).all() and dist_b.tobytes() == dist.tobytes()
+
+
+def test_from_graph_rejects_dangling_ids(abi):
+    pts = datagen.uniform(100, 8, 1)
+    zero = np.full((100, 64), 0xFFFFFFFF, dtype=np.uint32)
+    zero[3, 0] = 100  # == n: out of range
+    with pytest.raises(abi.IdbError) as e:
+        abi.Index.from_graph(pts, zero, [], 32)
+    assert e.value.status == abi.ERR_INVALID_ARG
+    zero[3, 0] = 99
+    up = np.full((40, 32), 0xFFFFFFFF, dtype=np.uint32)
+    up[0, 0] = 40  # upper rows may only name nodes of that layer
+    with pytest.raises(abi.IdbError):
+        abi.Index.from_graph(pts, zero, [up], 32)
+    up[0, 0] = 39
+    abi.Index.from_graph(pts, zero, [up], 32).close()
