@@ -93,6 +93,12 @@ cudaError_t fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+static uint32_t next_pow2(uint64_t v) {
+    uint32_t p = 1;
+    while (p < v && p < (1u << 30)) p <<= 1;
+    return p;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Scratch management
 // ---------------------------------------------------------------------------------------------------------
@@ -112,17 +118,13 @@ cudaError_t ensure_u32(uint32_t*& p, size_t& cap, size_t need) { return ensure(p
 cudaError_t ensure_u64(uint64_t*& p, size_t& cap, size_t need) { return ensure(p, cap, need); }
 cudaError_t ensure_f32(float*& p, size_t& cap, size_t need) { return ensure(p, cap, need); }
 
-static uint32_t next_pow2(uint64_t v) {
-    uint32_t p = 1;
-    while (p < v && p < (1u << 30)) p <<= 1;
-    return p;
-}
 
 idb_status Index::ensure_search_scratch(uint32_t ef, uint64_t nq, uint32_t k) {
     // visited tables: one per resident warp, sized for >= 2x the worst plausible number of visited ids (2M per expansion)
     uint32_t want_slots = std::max<uint32_t>(1024u, next_pow2((uint64_t)vis_mult * 2 * M * std::max<uint32_t>(ef, 16u)));
+    if (vis_slots_override) want_slots = vis_slots_override;  // tests: force the overflow -> retry path
     const uint32_t warps = (uint32_t)search_grid() * kSearchWarps;
-    if (want_slots > sc.gslots || !sc.vis_tables) {
+    if (want_slots > sc.gslots || !sc.vis_tables || (vis_slots_override && want_slots != sc.gslots)) {
         if (sc.vis_tables) cudaFree(sc.vis_tables);
         sc.vis_tables = nullptr;
         size_t words = (size_t)warps * want_slots;
@@ -323,6 +325,7 @@ idb_status Index::init_device(int dev) {
     if (const char* e = std::getenv("IDB_L2_PERSIST")) l2_persist = std::atoi(e) != 0;
     if (const char* e = std::getenv("IDB_CTAS_PER_SM")) ctas_per_sm = std::min(kMaxCtasPerSm, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("IDB_VARIANT")) variant = std::atoi(e);
+    if (const char* e = std::getenv("IDB_VIS_SLOTS")) vis_slots_override = next_pow2((uint64_t)std::max(64, std::atoi(e)));
     return IDB_OK;
 }
 

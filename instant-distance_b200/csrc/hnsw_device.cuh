@@ -31,7 +31,7 @@ constexpr int kSmallVisSlots = 512;           // shared-memory visited set used 
 constexpr int kTieCap = 1024;                 // per-warp tie list capacity (global memory)
 constexpr uint32_t kFullMask = 0xFFFFFFFFu;
 
-enum OptFlags : uint32_t { kOptPrefetchVectors = 1u, kOptPrefetchRows = 2u };
+enum OptFlags : uint32_t { kOptPrefetchVectors = 1u, kOptPrefetchRows = 2u, kOptPrefetchNextRow = 8u };
 
 enum QueryStatus : uint32_t { kQueryOk = 0, kQueryVisitedOverflow = 1, kQueryTieOverflow = 2 };
 
@@ -425,15 +425,23 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
             __syncwarp();
         } else {
             // ---- pop the min candidate: first unexpanded entry of nearest, else the smallest tie ----------
-            int sel = -1;
+            int sel = -1, nxt = -1;  // first / second unexpanded entry (the second is the likely NEXT candidate)
 #pragma unroll
             for (int t = 0; t < EF_T; ++t) {
-                if (sel < 0) {
+                if (nxt < 0) {
                     uint32_t idx = lane + 32 * t;
                     bool un = idx < s.cnt && !(near[idx] & kFlagExpanded);
                     uint32_t m = __ballot_sync(kFullMask, un);
-                    if (m) sel = 32 * t + __ffs(m) - 1;
+                    if (m && sel < 0) { sel = 32 * t + __ffs(m) - 1; m &= m - 1; }
+                    if (m && sel >= 0 && nxt < 0) nxt = 32 * t + __ffs(m) - 1;
                 }
+            }
+            if ((g.flags & kOptPrefetchNextRow) && nxt >= 0) {
+                // just-in-time L2 prefetch of the adjacency row we will most likely expand next (~one expansion ahead:
+                // short enough to survive the L2 turnover caused by the streaming point rows)
+                const uint32_t* r = rows + (size_t)key_pid(near[nxt]) * width;
+                if (lane == 0) prefetch_l2(r);
+                if (lane == 1 && links > 32) prefetch_l2(r + 32);
             }
             uint32_t cpid;
             if (sel >= 0) {

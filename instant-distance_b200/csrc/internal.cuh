@@ -97,6 +97,7 @@ struct Index {
     uint32_t vis_mult = 4;        // visited table slots = next_pow2(vis_mult * 2M * ef): load <= ~0.15, probe chains ~1
     bool l2_persist = false;      // pin the visited tables in L2 with an access-policy window
     int ctas_per_sm = kSearchCtasPerSm;
+    uint32_t vis_slots_override = 0; // IDB_VIS_SLOTS (tests): exact per-warp visited-table size, to force the overflow -> retry path
     int variant = 0;              // IDB_VARIANT: alternative (rows in flight, CTAs/SM) instantiations of K1
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -202,3 +202,19 @@ def test_concurrent_callers_share_one_index(abi, oracle):
     [t_.join() for t_ in th]
     for w, g_ in zip(want, got):
         assert (w[0] == g_[0]).all() and w[1].tobytes() == g_[1].tobytes()
+
+
+def test_visited_overflow_goes_through_the_retry_pass(abi, oracle, monkeypatch):
+    """A per-warp visited table that is too small aborts the query (kQueryVisitedOverflow); the device-side retry pass
+    re-runs it with a 2^21-slot table.  Results must still be the oracle's."""
+    pts = datagen.uniform(20_000, 16, 13)
+    ix, _ = oracle.build(pts, seed=3, threads=8)
+    g = ix.export()
+    q = datagen.uniform(300, 16, 14)
+    want = ix.search(q, ef_search=100, k=10, counters=True)
+    assert want[3][:, 3].max() > 1000  # more ids per query than 3/4 of the 1024-slot table below
+    monkeypatch.setenv("IDB_VIS_SLOTS", "1024")
+    gpu = abi.Index.from_graph(g.points, g.zero, g.upper, g.M)
+    got = gpu.search(q, ef_search=100, k=10)
+    assert (got[0] == want[0]).all() and got[1].tobytes() == want[1].tobytes() and (got[2] == want[2]).all()
+    assert (gpu.last_counters(len(q)) == want[3]).all()
