@@ -66,6 +66,11 @@ typedef struct idb_params {
     int32_t  device;            /* CUDA device ordinal */
     uint32_t storage;           /* IDB_STORAGE_F32 (default) or IDB_STORAGE_BF16: rows rounded to bf16 (RNE) and kept in HBM at
                                    half the bytes; distances still accumulate in fp32 in the same canonical order */
+    /* Builder::progress(ProgressBar) (core:70-75; feature `indicatif`): called on the building thread with the number of
+     * points whose insertion has been enqueued so far (set_position, core:519-525) and the total (set_length, core:216-222);
+     * the last call has done == total (finish, core:331-334).  NULL = no reporting. */
+    void (*progress)(uint64_t done, uint64_t total, void* user);
+    void*    progress_user;
 } idb_params;
 
 /* Builder::default() (core:101-113) — except `seed`, which the reference draws from entropy; here 0. */

@@ -413,6 +413,8 @@ idb_status idb_params_default(idb_params* p) {
     p->insert_batch = 0;
     p->device = 0;
     p->storage = IDB_STORAGE_F32;
+    p->progress = nullptr;
+    p->progress_user = nullptr;
     return IDB_OK;
 }
 

@@ -309,6 +309,7 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
             a.work_counter = reinterpret_cast<unsigned long long*>(bs.ctrl + 8);
             CUDA_TRY(build_dispatch_any(ch, a, l, st));
             g0 += b;
+            if (p.progress) p.progress(g0, n, p.progress_user);  // set_position (core:519-525)
         }
         if (layer != 0) {  // lib.rs:323-328
             snapshot_kernel<<<ix->num_sms * 4, 256, 0, st>>>(ix->d_zero, ix->d_upper[layer - 1], end, M);
@@ -318,6 +319,7 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
     uint32_t fails = 0;
     CUDA_TRY(cudaMemcpyAsync(&fails, bs.ctrl + 32, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (p.progress) p.progress(n, n, p.progress_user);  // finish (core:331-334)
     if (fails) return fail(IDB_ERR_CAPACITY, "%u inserts overflowed an internal per-insert structure (visited table / tie list)", fails);
     return IDB_OK;
 }

@@ -30,6 +30,7 @@ class Params(C.Structure):
         ("M", C.c_uint32), ("ef_construction", C.c_uint32), ("ef_search", C.c_uint32), ("ml", C.c_float),
         ("seed", C.c_uint64), ("heuristic", C.c_int32), ("extend_candidates", C.c_int32), ("keep_pruned", C.c_int32),
         ("insert_batch", C.c_uint32), ("device", C.c_int32), ("storage", C.c_uint32),
+        ("progress", C.c_void_p), ("progress_user", C.c_void_p),
     ]
 
 
@@ -117,6 +118,7 @@ def ptr(a, t):
 
 
 STORAGE = {"f32": 0, "bf16": 1}
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_uint64, C.c_uint64, C.c_void_p)
 
 
 def default_params(**kw):
@@ -162,10 +164,15 @@ class Index:
         return cls(h)
 
     @classmethod
-    def build(cls, rows, **kw):
+    def build(cls, rows, progress=None, **kw):
+        """progress: optional callable(done, total) — Builder::progress (lib.rs:70-75)."""
         rows = f32(rows)
         n, dim = rows.shape
         p = default_params(**kw)
+        cb = None
+        if progress is not None:
+            cb = PROGRESS_FN(lambda done, total, _user: progress(int(done), int(total)))
+            p.progress = C.cast(cb, C.c_void_p)
         ids = np.empty(n, dtype=np.uint32)
         h = C.c_void_p()
         check(lib().idb_build_f32(ptr(rows, C.c_float), n, dim, C.byref(p), C.byref(h), ptr(ids, C.c_uint32)))

@@ -17,6 +17,9 @@ struct IdbParams {
     keep_pruned: i32,
     insert_batch: u32,
     device: i32,
+    storage: u32,
+    progress: Option<extern "C" fn(done: u64, total: u64, user: *mut std::ffi::c_void)>,
+    progress_user: *mut std::ffi::c_void,
 }
 #[repr(C)]
 struct IdbIndex {

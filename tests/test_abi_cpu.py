@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     import ctypes as C
 
     abi = _abi()
-    assert C.sizeof(abi.Params) == 48  # 4*4 + 8 + 5*4 -> padded to 8
+    assert C.sizeof(abi.Params) == 64  # 4*4 + 8 + 5*4 + 4 (storage) + 2 pointers
     assert C.sizeof(abi.Info) == 8 + 16 + 32 * 8 + 8
     p = abi.default_params()
     assert (p.M, p.ef_construction, p.ef_search, p.heuristic, p.extend_candidates, p.keep_pruned) == (32, 100, 100, 1, 0, 1)

@@ -151,3 +151,12 @@ def test_build_argument_errors(abi):
     assert ix.info().n == 0 and ix.info().n_layers == 0
     got, dist, lens = ix.search(np.zeros((2, 8), dtype=np.float32), ef_search=10, k=3)
     assert (lens == 0).all() and (got == INV).all()
+
+
+def test_progress_callback(abi):
+    """Builder::progress (lib.rs:70-75, 216-222, 519-525, 331-334): monotone positions, finishes at the total."""
+    seen = []
+    ix, _ = abi.Index.build(datagen.uniform(5000, 8, 1), seed=1, progress=lambda done, total: seen.append((done, total)))
+    assert seen and all(t == 5000 for _, t in seen) and seen[-1][0] == 5000
+    assert all(a[0] <= b[0] for a, b in zip(seen, seen[1:]))
+    ix.close()
