@@ -141,6 +141,12 @@ IDB_API idb_status idb_index_load(const char* path, uint32_t dim, uint32_t M, in
 IDB_API idb_status idb_index_set_profiling(idb_index* index, int32_t enabled);
 IDB_API idb_status idb_index_last_kernel_ms(idb_index* index, float* out_ms, uint32_t* out_launches);
 
+/* Measurement only: random point-row gathers in K1's launch shape and arithmetic (no visited set / adjacency / merge), to show
+ * the gather ceiling of the device next to K1's own rate.  chain = independent 16-row batches between two dependent steps
+ * (0 = all independent).  *out_bytes = bytes gathered per run. */
+IDB_API idb_status idb_debug_gather_bench(idb_index* index, uint32_t n_items, uint32_t batches, uint32_t chain, uint32_t reps,
+                                          float* out_ms, double* out_bytes);
+
 IDB_API void* idb_index_stream(idb_index* index);      /* the cudaStream_t all work of this index is enqueued on */
 IDB_API idb_status idb_index_sync(idb_index* index);   /* cudaStreamSynchronize on it */
 IDB_API void idb_index_free(idb_index* index);         /* Drop for Hnsw */

@@ -1,0 +1,85 @@
+// debug_gather.cu — measurement-only: how fast can this GPU gather random point rows in K1's access pattern?
+//
+// One warp per work item, K1's launch shape (kSearchWarps warps per CTA, kSearchCtasPerSm CTAs per SM, persistent, items
+// claimed from an atomic counter).  Each item performs `batches` batches of NB row loads (NB rows in flight per lane, the
+// canonical lane_partial + batch_butterfly on them, exactly K1's batch_distances arithmetic) at pseudo-random PointIds.
+// `chain` batches are independent of each other, then the next group's ids depend on the previous group's result — that is
+// the dependency K1 has between expansions (chain = 3 at the headline config; chain = 0 means fully independent: the pure
+// gather ceiling).  No visited set, no adjacency rows, no merge: the gap between this and K1 is what those cost.
+#include "internal.cuh"
+
+namespace idb {
+
+template <int NB>
+__global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm)
+gather_bench_kernel(GraphView g, uint32_t n_items, uint32_t batches, uint32_t chain, unsigned long long* counter, float* sink) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t row_bytes = g.nchunks * 16u;
+    const char* lane_base = g.points + lane * 16;
+    const bool cok = (uint32_t)lane < g.nchunks;
+    float acc = 0.f;
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(counter, 1ull);
+        w = __shfl_sync(kFullMask, w, 0);
+        if (w >= n_items) break;
+        float4 q[1];
+        q[0] = cok ? __ldg(reinterpret_cast<const float4*>(lane_base + (size_t)((uint32_t)w % (uint32_t)g.n) * row_bytes)) : make_float4(0, 0, 0, 0);
+        uint32_t state = (uint32_t)w * 0x9E3779B1u + 12345u;
+        for (uint32_t b = 0; b < batches; ++b) {
+            float4 v[NB][1];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                uint32_t h = (state + (b * NB + i) * 0x85EBCA6Bu);
+                h ^= h >> 15; h *= 0xC2B2AE35u; h ^= h >> 13;
+                const uint32_t pid = h % (uint32_t)g.n;
+                v[i][0] = cok ? __ldg(reinterpret_cast<const float4*>(lane_base + (size_t)pid * row_bytes)) : make_float4(0, 0, 0, 0);
+            }
+            float p[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) p[i] = lane_partial<1>(q, v[i]);
+            const float total = batch_butterfly<NB>(p, lane);
+            acc += total;
+            if (chain && (b + 1) % chain == 0) state = state * 1664525u + __float_as_uint(__shfl_sync(kFullMask, total, 0));  // dependency
+        }
+    }
+    if (acc == 123456.789f) sink[0] = acc;  // keep the work alive
+}
+
+}  // namespace idb
+
+using namespace idb;
+
+extern "C" idb_status idb_debug_gather_bench(idb_index* index, uint32_t n_items, uint32_t batches, uint32_t chain, uint32_t reps,
+                                             float* out_ms, double* out_bytes) {
+    if (!index || !out_ms) return fail(IDB_ERR_INVALID_ARG, "null argument");
+    Index* ix = reinterpret_cast<Index*>(index);
+    if (ix->bf16 || ix->nchunks > 32 || ix->n == 0) return fail(IDB_ERR_UNSUPPORTED, "gather bench: f32 rows of <= 128 floats only");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CUDA_TRY(cudaSetDevice(ix->device));
+    unsigned long long* d_counter = nullptr;
+    float* d_sink = nullptr;
+    CUDA_TRY(cudaMalloc(&d_counter, 8));
+    CUDA_TRY(cudaMalloc(&d_sink, 4));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (uint32_t r = 0; r < reps + 1; ++r) {
+        CUDA_TRY(cudaMemsetAsync(d_counter, 0, 8, ix->stream));
+        CUDA_TRY(cudaEventRecord(e0, ix->stream));
+        gather_bench_kernel<16><<<ix->search_grid(), kSearchWarps * 32, 0, ix->stream>>>(ix->view(), n_items, batches, chain, d_counter, d_sink);
+        CUDA_TRY(cudaEventRecord(e1, ix->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (r > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_counter);
+    cudaFree(d_sink);
+    *out_ms = best;
+    if (out_bytes) *out_bytes = (double)n_items * batches * 16.0 * ix->nchunks * 16.0;
+    return IDB_OK;
+}

@@ -1,0 +1,25 @@
+"""Gather ceiling next to K1 (measurement only): random 512-byte row gathers in K1's launch shape, with 0 / 3 / 1 independent
+16-row batches between dependent steps.  Prints GB/s per setting for a 1M x 128 f32 index."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "instant-distance_b200", "python"))
+import numpy as np  # noqa: E402
+
+from instant_distance_b200 import _abi  # noqa: E402
+from tests import datagen  # noqa: E402
+
+n = 1_000_000
+pts = datagen.sift_shaped(n, 128, 1)
+zero = np.full((n, 64), 0xFFFFFFFF, dtype=np.uint32)
+for ctas in ("4", "3", "2"):
+    os.environ["IDB_CTAS_PER_SM"] = ctas
+    ix = _abi.Index.from_graph(pts, zero, [], 32)
+    for chain in (0, 6, 3, 1):
+        ms, by = ix.gather_bench(n_items=10000, batches=288, chain=chain, reps=3)
+        print(json.dumps({"ctas_per_sm": int(ctas), "warps_per_sm": int(ctas) * 4, "chain": chain, "ms": ms, "GBps": by / (ms / 1e3) / 1e9,
+                          "frac_of_6572": by / (ms / 1e3) / 1e9 / 6572.5}), flush=True)
+    ix.close()
