@@ -124,12 +124,17 @@ idb_status Index::ensure_search_scratch(uint32_t ef, uint64_t nq, uint32_t k) {
     uint32_t want_slots = std::max<uint32_t>(1024u, next_pow2((uint64_t)vis_mult * 2 * M * std::max<uint32_t>(ef, 16u)));
     if (vis_slots_override) want_slots = vis_slots_override;  // tests: force the overflow -> retry path
     const uint32_t warps = (uint32_t)search_grid() * kSearchWarps;
-    if (want_slots > sc.gslots || !sc.vis_tables || (vis_slots_override && want_slots != sc.gslots)) {
+    // bitmap flavour of the big tier: n bits per warp, used when that is no bigger than twice the hash table
+    const uint32_t bm_words = (uint32_t)std::min<uint64_t>(((n + 31) / 32 + 127) / 128 * 128, 0xFFFFFF80u);
+    sc.bm_words = (vis_bitmap && !vis_slots_override && (n + 31) / 32 <= 2ull * want_slots) ? bm_words : 0u;
+    const uint32_t want_stride = std::max(want_slots, sc.bm_words);
+    if (want_slots > sc.gslots || want_stride > sc.vis_stride || !sc.vis_tables || (vis_slots_override && want_slots != sc.gslots)) {
         if (sc.vis_tables) cudaFree(sc.vis_tables);
         sc.vis_tables = nullptr;
-        size_t words = (size_t)warps * want_slots;
+        size_t words = (size_t)warps * want_stride;
         CUDA_TRY(cudaMalloc(&sc.vis_tables, words * 4));
         CUDA_TRY(fill_u32(sc.vis_tables, words, kInvalid, stream));
+        sc.vis_stride = want_stride;
         sc.gslots = want_slots;
         if (l2_persist) {
             // Keep the per-warp visited tables resident in L2: point rows stream through once, the tables are hit
@@ -193,8 +198,10 @@ idb_status Index::enqueue_search(const float* d_queries_padded, uint64_t nq, uin
     a.fail_count = reinterpret_cast<uint32_t*>(sc.ctrl + 16);
     a.fail_list = sc.fail_list;
     a.vis_tables = sc.vis_tables;
-    a.gslots = sc.gslots;
+    a.gslots = sc.bm_words ? sc.bm_words : sc.gslots;
     a.gshift = 32 - (uint32_t)std::log2((double)sc.gslots);
+    a.vis_stride = sc.vis_stride;
+    a.vis_bitmap = sc.bm_words ? 1u : 0u;
     a.tie_tables = sc.tie_tables;
     a.variant = variant;
     a.out_keys = pending_out_keys;
@@ -225,6 +232,8 @@ idb_status Index::enqueue_search(const float* d_queries_padded, uint64_t nq, uin
     r.vis_tables = sc.retry_tables;
     r.gslots = kRetrySlots;
     r.gshift = 32 - 21;
+    r.vis_stride = kRetrySlots;
+    r.vis_bitmap = 0;
     r.tie_tables = sc.tie_tables + (size_t)search_grid() * kSearchWarps * kTieCap;
     CUDA_TRY(dispatch_search(r, ch, row_t, ef_t, kRetryWarps / kSearchWarps, stream));
     last_nq = nq;
@@ -325,6 +334,7 @@ idb_status Index::init_device(int dev) {
     if (const char* e = std::getenv("IDB_L2_PERSIST")) l2_persist = std::atoi(e) != 0;
     if (const char* e = std::getenv("IDB_CTAS_PER_SM")) ctas_per_sm = std::min(kMaxCtasPerSm, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("IDB_VARIANT")) variant = std::atoi(e);
+    if (const char* e = std::getenv("IDB_VIS_BITMAP")) vis_bitmap = std::atoi(e);
     if (const char* e = std::getenv("IDB_VIS_SLOTS")) vis_slots_override = next_pow2((uint64_t)std::max(64, std::atoi(e)));
     return IDB_OK;
 }

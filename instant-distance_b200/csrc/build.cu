@@ -258,6 +258,7 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
     a.fail_count = reinterpret_cast<uint32_t*>(bs.ctrl + 32);
     a.vis_tables = ix->sc.vis_tables;
     a.gslots = ix->sc.gslots;
+    a.vis_stride = ix->sc.vis_stride;
     a.gshift = 32 - (uint32_t)std::log2((double)ix->sc.gslots);
     a.tie_tables = ix->sc.tie_tables;
     a.sorted_pairs = bs.sorted;

@@ -38,6 +38,7 @@ struct BuildArgs {
     unsigned long long* work_counter;
     uint32_t* vis_tables;
     uint32_t gslots, gshift;
+    uint32_t vis_stride;               // words between consecutive warps' tables (>= gslots)
     uint64_t* tie_tables;
     // relink
     const uint64_t* sorted_pairs;   // count*2M sorted ascending
@@ -178,9 +179,11 @@ __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) insert_se
     s.vis.small = reinterpret_cast<uint32_t*>(base + kNearBytes);
     s.cpid = s.vis.small + kSmallVisSlots;
     s.ckey = reinterpret_cast<uint64_t*>(s.cpid + 128);
-    s.vis.big = a.vis_tables + (size_t)gwarp * a.gslots;
+    s.land = nullptr;
+    s.vis.big = a.vis_tables + (size_t)gwarp * a.vis_stride;
     s.vis.gslots = a.gslots;
     s.vis.gshift = a.gshift;
+    s.vis.bitmap = false;
     s.vis.count = 0;
     s.vis.use_big = false;
     s.ties = a.tie_tables + (size_t)gwarp * kTieCap;

@@ -15,6 +15,8 @@ namespace idb {
 constexpr int kSearchWarps = 4;        // warps (= live queries) per CTA
 constexpr int kSearchCtasPerSm = 4;    // resident CTAs per SM -> 16 live queries per SM, <= 128 registers per thread
 constexpr int kMaxCtasPerSm = 8;       // upper bound over the tuning variants (scratch is sized for it)
+constexpr int kVariantLand = 5;       // IDB_VARIANT: K1 with the shared-memory landing zone (2*B rows in flight per trip)
+constexpr int kVariantLandSpec = 6;   // ... plus speculative loads of the first B row entries while the visited probes are outstanding
 constexpr int kRetryWarps = 32;        // warps of the (normally idle) overflow-retry pass
 constexpr uint32_t kRetrySlots = 1u << 21;
 
@@ -45,7 +47,9 @@ struct SearchArgs {
     uint32_t* fail_count;
     uint32_t* fail_list;               // may be null (retry pass)
     uint32_t* vis_tables;
-    uint32_t gslots, gshift;
+    uint32_t gslots, gshift;           // hash flavour: slots (power of two) / 32 - log2(slots); bitmap flavour: words in use / unused
+    uint32_t vis_stride;               // words between consecutive warps' tables (>= gslots)
+    uint32_t vis_bitmap;               // big visited tier is a bitmap over PointIds (hnsw_device.cuh VisitedSet::bitmap)
     uint64_t* tie_tables;
     uint64_t* out_keys;                // optional: nq x k packed (distance bits << 32 | id_map[pid]) for the sharded all-gather
     const uint32_t* id_map;            // optional: PointId -> caller's global row id
@@ -54,7 +58,9 @@ struct SearchArgs {
 
 struct Scratch {
     uint32_t* vis_tables = nullptr;
-    uint32_t gslots = 0;
+    uint32_t gslots = 0;          // hash slots per warp (power of two)
+    uint32_t bm_words = 0;        // != 0: K1 uses the bitmap flavour with this many words per warp
+    uint32_t vis_stride = 0;      // words per warp actually allocated (>= gslots; >= bitmap words when the bitmap flavour is on)
     uint32_t* retry_tables = nullptr;
     uint64_t* tie_tables = nullptr;
     unsigned char* ctrl = nullptr;
@@ -98,6 +104,7 @@ struct Index {
     bool l2_persist = false;      // pin the visited tables in L2 with an access-policy window
     int ctas_per_sm = kSearchCtasPerSm;
     uint32_t vis_slots_override = 0; // IDB_VIS_SLOTS (tests): exact per-warp visited-table size, to force the overflow -> retry path
+    int vis_bitmap = 0;           // IDB_VIS_BITMAP: 0 hash set, 1 bitmap over PointIds when it is no bigger than 2x the hash table
     int variant = 0;              // IDB_VARIANT: alternative (rows in flight, CTAs/SM) instantiations of K1
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
