@@ -179,7 +179,6 @@ __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) insert_se
     s.vis.small = reinterpret_cast<uint32_t*>(base + kNearBytes);
     s.cpid = s.vis.small + kSmallVisSlots;
     s.ckey = reinterpret_cast<uint64_t*>(s.cpid + 128);
-    s.land = nullptr;
     s.vis.big = a.vis_tables + (size_t)gwarp * a.vis_stride;
     s.vis.gslots = a.gslots;
     s.vis.gshift = a.gshift;

@@ -192,8 +192,8 @@ __device__ __forceinline__ bool vis_insert_big(uint32_t* tab, uint32_t gshift, u
     }
 }
 
-// Bitmap flavour of the big tier (used when n / 32 words is no bigger than the hash table would be): one atomic per id,
-// no probe chains, never overflows.
+// Bitmap flavour of the big tier (used when n / 32 words is no bigger than twice the hash table): one atomic per id,
+// no probe chains (with the hash set ~every row has at least one lane that needs a second, dependent probe), never overflows.
 __device__ __forceinline__ uint32_t vis_bitmap_fetch_clear(uint32_t* tab, uint32_t pid) {
     return atomicAnd(tab + (pid >> 5), ~(1u << (pid & 31)));
 }
@@ -280,7 +280,6 @@ struct WarpState {
     uint32_t* cpid;          // shared: 128 compacted new ids of the current row
     uint64_t* ckey;          // shared: their 128 keys (canonical distance bits << 32 | pid)
     uint64_t* ties;          // global: kTieCap keys
-    unsigned char* land;     // shared: landing zone of B rows for cp.async row loads (LAND variants), else null
     int cur;                 // live near buffer
     uint32_t cnt;            // len(nearest)
     uint32_t ntie;
@@ -298,34 +297,17 @@ __device__ __forceinline__ uint32_t lower_bound_keys(const uint64_t* a, uint32_t
     return lo;
 }
 
-// cp.async (LDGSTS) of this lane's chunk of a row into the warp's shared-memory landing zone: the bytes are in flight
-// without holding registers, so a warp can have NB rows in flight in registers AND NB more in shared memory.
-// `ok == false` zero-fills (src-size 0: the source is not read).
-template <uint32_t kBytes>
-__device__ __forceinline__ void cp_async_chunk(void* smem_dst, const void* gsrc, bool ok) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    const uint32_t sz = ok ? kBytes : 0u;
-    if constexpr (kBytes == 16)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
-    else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 // Distances from q to the n_new points listed in cpid (shared, 16-byte aligned), NB rows in flight per lane; writes the
 // keys (canonical distance bits << 32 | pid) to ckey.  The only place in the traversal that touches point rows.
 // kFull: every lane owns a real chunk in every one of its CH slots (dim is a multiple of 128) -> no chunk predicates.
-// LAND: `land` is a per-warp shared-memory landing zone of NB rows (NB * CH * 32 chunks): each trip issues NB rows as
-// register loads and the next NB rows as cp.async into the landing zone, i.e. 2*NB rows in flight per round trip;
-// each lane copies and later reads back only its own chunks, so no cross-lane synchronisation is involved.
-// spec (LAND only): the rows of the first NB ROW ENTRIES were already put in flight into the landing zone while the
-// visited probes were outstanding (speculate_rows); `spec_fresh` = which of those entries turned out to be new (they are the
-// first popc(spec_fresh) compacted entries, in the same order) and `ent0` = this lane's own row entry.
-template <int CH, int NB, bool kFull, class RT, bool LAND>
+// `hook(trip)` runs once per trip right after that trip's row loads have been issued (its own memory operations then
+// overlap them); search_layer uses it to work ahead on the predicted next candidate (NextSpec below).
+struct NoTripHook {
+    __device__ __forceinline__ void operator()(uint32_t) const {}
+};
+template <int CH, int NB, bool kFull, class RT, class Hook>
 __device__ __forceinline__ void batch_distances_impl(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid,
-                                                     uint64_t* ckey, uint32_t n_new, int lane, unsigned char* land,
-                                                     bool spec, uint32_t spec_fresh, uint32_t ent0) {
+                                                     uint64_t* ckey, uint32_t n_new, int lane, Hook& hook) {
     const uint32_t row_bytes = g.nchunks * RT::kChunkBytes;
     const char* lane_base = g.points + lane * RT::kChunkBytes;
     if (g.flags & kOptPrefetchVectors) {  // pull every row of this expansion into L2 now; the batches below then hit L2
@@ -337,99 +319,115 @@ __device__ __forceinline__ void batch_distances_impl(const GraphView& g, const f
     bool cok[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) cok[j] = kFull || (uint32_t)(lane + 32 * j) < g.nchunks;
-    unsigned char* lane_land = land + lane * RT::kChunkBytes;
-    // Groups of <= NB rows: h = 0 register loads, h = 1 landing-zone half of the same trip, h = 2 the speculative group.
-    uint32_t b0 = 0;
-    int h = (LAND && spec) ? 2 : 0;
-    bool second = false;
 #pragma unroll 1
-    for (;;) {
-        if (h == 0) {
-            if (b0 >= n_new) break;
-            second = LAND && (n_new - b0) > (uint32_t)NB;  // uniform: this trip also has a landing-zone half
-            if (LAND && second) {
-                const uint32_t nb2 = n_new - b0 - NB;
-#pragma unroll
-                for (int i = 0; i < NB; ++i) {
-                    const bool ok = (uint32_t)i < nb2;
-                    const char* row = lane_base + (size_t)(ok ? cpid[b0 + NB + i] : 0u) * row_bytes;
-#pragma unroll
-                    for (int j = 0; j < CH; ++j)
-                        cp_async_chunk<RT::kChunkBytes>(lane_land + (i * CH + j) * 32 * RT::kChunkBytes,
-                                                        row + j * 32 * RT::kChunkBytes, ok && cok[j]);
-                }
-                cp_async_commit();
-            }
-        }
-        const uint32_t base = b0 + (h == 1 ? NB : 0);
-        const uint32_t nb = n_new - base;  // rows in this group (uniform); entries i >= nb are predicated off
+    for (uint32_t b0 = 0; b0 < n_new; b0 += NB) {
+        const uint32_t nb = n_new - b0;  // rows in this batch (uniform); entries i >= nb are predicated off
         typename RT::Raw v[NB][CH];
-        if (!LAND || h == 0) {
 #pragma unroll
-            for (int i = 0; i < NB; ++i) {
-                // branch-free on purpose: `if (i < nb) {load; use}` makes ptxas emit two branches per row
-                const bool ok = (uint32_t)i < nb;
-                const char* row = lane_base + (size_t)cpid[base + i] * row_bytes;  // shared-memory broadcast of the id
+        for (int i = 0; i < NB; ++i) {
+            // branch-free on purpose: `if (i < nb) {load; use}` makes ptxas emit two branches per row
+            const bool ok = (uint32_t)i < nb;
+            const char* row = lane_base + (size_t)cpid[b0 + i] * row_bytes;  // shared-memory broadcast of the id
 #pragma unroll
-                for (int j = 0; j < CH; ++j)
-                    v[i][j] = (ok && cok[j]) ? RT::ld_raw(row + j * 32 * RT::kChunkBytes) : RT::zero();
-            }
-        } else {
-            cp_async_wait_all();
-#pragma unroll
-            for (int i = 0; i < NB; ++i)
-#pragma unroll
-                for (int j = 0; j < CH; ++j)
-                    v[i][j] = *reinterpret_cast<const typename RT::Raw*>(lane_land + (i * CH + j) * 32 * RT::kChunkBytes);
+            for (int j = 0; j < CH; ++j)
+                v[i][j] = (ok && cok[j]) ? RT::ld_raw(row + j * 32 * RT::kChunkBytes) : RT::zero();
         }
+        hook(b0 / NB);
         float p[NB];
 #pragma unroll
         for (int i = 0; i < NB; ++i) p[i] = lane_partial_raw<CH, RT>(q, v[i]);
         const float total = batch_butterfly<NB>(p, lane);
-        if (LAND && h == 2) {
-            // lane l < NB holds the distance of row entry l; fresh entries keep their row order in the compacted list
-            if (lane < NB && ((spec_fresh >> lane) & 1u)) ckey[__popc(spec_fresh & ((1u << lane) - 1))] = mk_key(total, ent0);
-            b0 = __popc(spec_fresh);
-            h = 0;
-        } else {
-            if ((uint32_t)lane < nb && lane < NB) ckey[base + lane] = mk_key(total, cpid[base + lane]);
-            if (LAND && h == 0 && second) {
-                h = 1;
-            } else {
-                b0 += (LAND && second) ? 2 * NB : NB;
-                h = 0;
-            }
-        }
+        if ((uint32_t)lane < nb && lane < NB) ckey[b0 + lane] = mk_key(total, cpid[b0 + lane]);
     }
     __syncwarp();
 }
-template <int CH, int NB, class RT = RowF32, bool LAND = false>
+template <int CH, int NB, class RT, class Hook>
 __device__ __forceinline__ void batch_distances(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid, uint64_t* ckey,
-                                                uint32_t n_new, int lane, unsigned char* land = nullptr, bool spec = false,
-                                                uint32_t spec_fresh = 0, uint32_t ent0 = 0) {
+                                                uint32_t n_new, int lane, Hook& hook) {
     // (a second, predicate-free instantiation for dim % 128 == 0 was tried: the two inlined copies made ptxas spill)
-    batch_distances_impl<CH, NB, false, RT, LAND>(g, q, cpid, ckey, n_new, lane, land, spec, spec_fresh, ent0);
+    batch_distances_impl<CH, NB, false, RT, Hook>(g, q, cpid, ckey, n_new, lane, hook);
+}
+template <int CH, int NB, class RT = RowF32>
+__device__ __forceinline__ void batch_distances(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid, uint64_t* ckey,
+                                                uint32_t n_new, int lane) {
+    NoTripHook none;
+    batch_distances_impl<CH, NB, false, RT, NoTripHook>(g, q, cpid, ckey, n_new, lane, none);
 }
 
-// While the visited probes of a row are outstanding, put the point rows of its first NB entries in flight into the landing
-// zone (they are new ~70 % of the time; the others are wasted traffic, which is why this is a tuning variant).
-template <int CH, int NB, class RT>
-__device__ __forceinline__ void speculate_rows(const GraphView& g, uint32_t ent0, uint32_t count, int lane, unsigned char* land) {
-    const uint32_t row_bytes = g.nchunks * RT::kChunkBytes;
-    const char* lane_base = g.points + lane * RT::kChunkBytes;
-    unsigned char* lane_land = land + lane * RT::kChunkBytes;
+// ---------------------------------------------------------------------------------------------------------
+// Working ahead on the NEXT candidate (PIPE variants of search_layer; bitmap visited tier only).
+// The candidate popped next is, ~80 % of the time, the second unexpanded entry of `nearest` as it stood at the current pop
+// (it changes only if this expansion admits something closer).  So while the distance trips of the current expansion are
+// in flight the warp (1) loads that entry's adjacency row and, one trip later, (2) issues the visited test-and-set of its
+// row entries.  Both round trips then overlap the row gathers instead of following them.  This is exact:
+//   * the speculative test-and-sets are issued after the current expansion's own ones have settled, i.e. in the order the
+//     sequential algorithm would perform them if the prediction holds;
+//   * if another candidate is popped instead, exactly the bits this speculation cleared are set again (atomicOr) before
+//     any other visited operation; nothing else reads the per-warp bitmap in between;
+//   * on leaving the layer an unconsumed speculation is rolled back the same way.
+// ---------------------------------------------------------------------------------------------------------
+template <int ROW_T>
+struct NextSpec {
+    uint32_t want;           // PointId to work ahead on during the coming trips; kInvalid = none
+    uint32_t pid;            // PointId whose row is held in ent[]; kInvalid = none
+    uint32_t ent[ROW_T];     // this lane's entries of that row
+    uint32_t old[ROW_T];     // results of the speculative visited test-and-sets (valid iff probed)
+    uint32_t count;          // NearestIter length of that row (valid iff probed)
+    bool probed;
+};
+template <int ROW_T>
+__device__ __forceinline__ uint32_t row_count(const uint32_t (&ent)[ROW_T]) {  // first INVALID (types.rs:178-191)
+    uint32_t count = 32 * ROW_T;
 #pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        const uint32_t pid = __shfl_sync(kFullMask, ent0, i);
-        const bool ok = (uint32_t)i < count;
-        const char* row = lane_base + (size_t)(ok ? pid : 0u) * row_bytes;
-#pragma unroll
-        for (int j = 0; j < CH; ++j)
-            cp_async_chunk<RT::kChunkBytes>(lane_land + (i * CH + j) * 32 * RT::kChunkBytes, row + j * 32 * RT::kChunkBytes,
-                                            ok && (uint32_t)(lane + 32 * j) < g.nchunks);
+    for (int t = ROW_T - 1; t >= 0; --t) {
+        uint32_t m = __ballot_sync(kFullMask, ent[t] == kInvalid);
+        if (m) count = 32 * t + __ffs(m) - 1;
     }
-    cp_async_commit();
+    return count;
 }
+template <int ROW_T>
+__device__ __forceinline__ void spec_rollback(NextSpec<ROW_T>& sp, VisitedSet& vis, int lane) {
+    if (sp.pid != kInvalid && sp.probed) {
+#pragma unroll
+        for (int t = 0; t < ROW_T; ++t)
+            if ((uint32_t)(lane + 32 * t) < sp.count && ((sp.old[t] >> (sp.ent[t] & 31)) & 1u))
+                atomicOr(vis.big + (sp.ent[t] >> 5), 1u << (sp.ent[t] & 31));
+        __syncwarp();  // orders these before the test-and-sets other lanes issue next (same words are likely)
+    }
+    sp.pid = kInvalid;
+    sp.probed = false;
+}
+template <int ROW_T>
+struct SpecTripHook {
+    NextSpec<ROW_T>& sp;
+    VisitedSet& vis;
+    const uint32_t* rows;
+    uint32_t width, links;
+    int lane;
+    __device__ __forceinline__ void operator()(uint32_t trip) {
+        if (sp.want == kInvalid) return;
+        if (trip == 0) {
+            const uint32_t* row = rows + (size_t)sp.want * width;
+#pragma unroll
+            for (int t = 0; t < ROW_T; ++t) {
+                const uint32_t e = lane + 32 * t;
+                sp.ent[t] = kInvalid;
+                if (e < links) sp.ent[t] = __ldg(row + e);
+            }
+            sp.pid = sp.want;
+            sp.probed = false;
+        } else if (trip == 1) {
+            sp.count = row_count<ROW_T>(sp.ent);
+#pragma unroll
+            for (int t = 0; t < ROW_T; ++t) {
+                sp.old[t] = 0u;
+                if ((uint32_t)(lane + 32 * t) < sp.count) sp.old[t] = vis_bitmap_fetch_clear(vis.big, sp.ent[t]);
+            }
+            sp.probed = true;
+        }
+    }
+};
+
 
 // Rare path: something was evicted while its distance equals the new furthest distance.  Such an entry stays a
 // live candidate in the reference (strict `>` at lib.rs:601) iff it is unexpanded and had been ADMITTED
@@ -514,18 +512,25 @@ __device__ __forceinline__ uint64_t pop_min_tie(WarpState& s, int lane) {
 // kLive: rows may be rewritten concurrently (GPU build) -> read them through L2 (ld.global.cg), not the
 // read-only/L1 path.
 // ---------------------------------------------------------------------------------------------------------
-template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT, bool LAND, bool SPEC>
+template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT, bool PIPE>
 __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, const float4 (&q)[CH], const uint32_t* rows,
                                              uint32_t width, uint32_t links, uint32_t ef_cur, bool seed_entry, int lane) {
     const uint32_t lt_mask = (1u << lane) - 1;
+    NextSpec<ROW_T> sp;
+    sp.want = kInvalid;
+    sp.pid = kInvalid;
+    sp.probed = false;
+    sp.count = 0;
+#pragma unroll
+    for (int t = 0; t < ROW_T; ++t) sp.ent[t] = kInvalid, sp.old[t] = 0u;
+    SpecTripHook<ROW_T> spec_hook{sp, s.vis, rows, width, links, lane};
     for (;;) {
         uint64_t* near = (s.near_base + s.cur * s.near_len);
         uint32_t n_new = 0;
-        bool spec = false;          // SPEC: rows of the first B row entries are already in flight into the landing zone
-        uint32_t spec_fresh = 0, ent0 = 0;
         if (seed_entry) {
             // push(PointId(0)) (lib.rs:364 / 444): the entry point is the only "row entry" of a pseudo expansion
             seed_entry = false;
+            sp.want = kInvalid;
             vis_insert(s.vis, 0u, lane == 0);
             s.vis.count = 1;
             if (lane == 0) s.cpid[0] = 0u;
@@ -565,33 +570,43 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
                 break;  // heap empty, or its min is strictly beyond the furthest result (lib.rs:601-603)
             }
             s.n_expand++;
+            // work ahead on the second unexpanded entry (the likely next candidate) during this expansion's trips
+            sp.want = (PIPE && !kLive && s.vis.use_big && s.vis.bitmap && nxt >= 0) ? key_pid(near[nxt]) : kInvalid;
+            bool hit = false;
+            if constexpr (PIPE) {
+                hit = sp.pid == cpid;            // uniform
+                if (!hit) spec_rollback(sp, s.vis, lane);
+            }
 
             // ---- row of the candidate: NearestIter stops at the first INVALID (types.rs:178-191) ----------
             uint32_t ent[ROW_T];
-            const uint32_t* row = rows + (size_t)cpid * width;
+            if (PIPE && hit) {
 #pragma unroll
-            for (int t = 0; t < ROW_T; ++t) {
-                uint32_t e = lane + 32 * t;
-                ent[t] = kInvalid;
-                if (e < links) ent[t] = kLive ? __ldcg(row + e) : __ldg(row + e);
-            }
-            uint32_t count = 32 * ROW_T;
+                for (int t = 0; t < ROW_T; ++t) ent[t] = sp.ent[t];
+            } else {
+                const uint32_t* row = rows + (size_t)cpid * width;
 #pragma unroll
-            for (int t = ROW_T - 1; t >= 0; --t) {
-                uint32_t m = __ballot_sync(kFullMask, ent[t] == kInvalid);
-                if (m) count = 32 * t + __ffs(m) - 1;
+                for (int t = 0; t < ROW_T; ++t) {
+                    uint32_t e = lane + 32 * t;
+                    ent[t] = kInvalid;
+                    if (e < links) ent[t] = kLive ? __ldcg(row + e) : __ldg(row + e);
+                }
             }
+            const bool pre = PIPE && hit && sp.probed;  // its visited test-and-sets are already done (or in flight)
+            const uint32_t count = pre ? sp.count : row_count<ROW_T>(ent);
+            sp.pid = kInvalid;
+            sp.probed = false;
             if (count == 0) continue;
 
             // ---- visited.insert for every row entry (lib.rs:705), compacted in row order ------------------
             if (!vis_reserve(s.vis, count, lane)) { s.status = kQueryVisitedOverflow; break; }
             VisProbe probe[ROW_T];
+            if (pre) {
 #pragma unroll
-            for (int t = 0; t < ROW_T; ++t) probe[t] = vis_probe(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count);
-            if constexpr (LAND && SPEC) {
-                spec = s.vis.use_big;  // the wide layer only (the ef = 1 layers have short rows and small tables)
-                if (spec) speculate_rows<CH, B, RT>(g, ent[0], count, lane, s.land);
-                ent0 = ent[0];
+                for (int t = 0; t < ROW_T; ++t) probe[t].old = sp.old[t], probe[t].h = ent[t] >> 5;
+            } else {
+#pragma unroll
+                for (int t = 0; t < ROW_T; ++t) probe[t] = vis_probe(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count);
             }
 #pragma unroll
             for (int t = 0; t < ROW_T; ++t) {
@@ -599,19 +614,16 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
                 const uint32_t m = __ballot_sync(kFullMask, fresh);
                 if (fresh) s.cpid[n_new + __popc(m & lt_mask)] = ent[t];
                 n_new += __popc(m);
-                if (LAND && SPEC && t == 0) spec_fresh = m & ((1u << B) - 1u);
             }
             s.vis.count += n_new;
             s.n_dist += n_new;
-            if (n_new == 0) {
-                if (LAND && SPEC && spec) cp_async_wait_all();  // nothing was new: drain the speculative copies before the zone is reused
-                continue;
-            }
+            if (n_new == 0) continue;
             __syncwarp();
         }
 
         // ---- distances (lib.rs:709-710) --------------------------------------------------------------------
-        batch_distances<CH, B, RT, LAND>(g, q, s.cpid, s.ckey, n_new, lane, s.land, spec, spec_fresh, ent0);
+        if constexpr (PIPE) batch_distances<CH, B, RT>(g, q, s.cpid, s.ckey, n_new, lane, spec_hook);
+        else batch_distances<CH, B, RT>(g, q, s.cpid, s.ckey, n_new, lane);
         uint64_t keyg[ROW_T];
 #pragma unroll
         for (int gi = 0; gi < ROW_T; ++gi) {
@@ -708,6 +720,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
             if (s.status != kQueryOk) break;
         }
     }
+    if constexpr (PIPE) spec_rollback(sp, s.vis, lane);  // an unconsumed speculation leaves the visited set exact
 }
 
 // Search::cull (lib.rs:729-737): candidates := nearest; visited := {pids of nearest}.
@@ -732,7 +745,7 @@ __device__ __forceinline__ void cull(WarpState& s, int lane, bool next_big) {
 // Construction::insert's descent (lib.rs:443-463) when target_layer = the insert layer, ef_target = ef_construction.
 // Layers above the target are searched on the UpperNode snapshots with ef = 1; the target layer on the zero table.
 // On return nearest = (s.near_base + s.cur * s.near_len)[0..s.cnt).  counters (if non-null): {n_expand_upper, n_dist_upper, n_expand_target, n_dist_target}.
-template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT = RowF32, bool LAND = false, bool SPEC = false>
+template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT = RowF32, bool PIPE = false>
 __device__ __forceinline__ void descend(const GraphView& g, WarpState& s, const float4 (&q)[CH], uint32_t target_layer,
                                         uint32_t ef_target, int lane, uint32_t* counters4) {
     s.cur = 0;
@@ -751,7 +764,7 @@ __device__ __forceinline__ void descend(const GraphView& g, WarpState& s, const 
         const uint32_t* rows = above ? g.upper[cur - 1] : g.zero;
         const uint32_t width = above ? g.M : 2 * g.M;
         const uint32_t links = (above || target_layer != 0) ? g.M : 2 * g.M;  // lib.rs:445 / 366-369
-        search_layer<CH, ROW_T, EF_T, B, kLive, RT, LAND, SPEC>(g, s, q, rows, width, links, above ? 1u : ef_target, seed, lane);
+        search_layer<CH, ROW_T, EF_T, B, kLive, RT, PIPE>(g, s, q, rows, width, links, above ? 1u : ef_target, seed, lane);
         seed = false;
         if (!above || s.status != kQueryOk) break;
         cull<EF_T>(s, lane, /*next_big=*/(cur - 1 == target_layer));

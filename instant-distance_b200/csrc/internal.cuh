@@ -15,8 +15,7 @@ namespace idb {
 constexpr int kSearchWarps = 4;        // warps (= live queries) per CTA
 constexpr int kSearchCtasPerSm = 4;    // resident CTAs per SM -> 16 live queries per SM, <= 128 registers per thread
 constexpr int kMaxCtasPerSm = 8;       // upper bound over the tuning variants (scratch is sized for it)
-constexpr int kVariantLand = 5;       // IDB_VARIANT: K1 with the shared-memory landing zone (2*B rows in flight per trip)
-constexpr int kVariantLandSpec = 6;   // ... plus speculative loads of the first B row entries while the visited probes are outstanding
+constexpr int kVariantNoPipe = 7;     // IDB_VARIANT: K1 without working ahead on the next candidate (A/B measurement)
 constexpr int kRetryWarps = 32;        // warps of the (normally idle) overflow-retry pass
 constexpr uint32_t kRetrySlots = 1u << 21;
 
@@ -104,7 +103,7 @@ struct Index {
     bool l2_persist = false;      // pin the visited tables in L2 with an access-policy window
     int ctas_per_sm = kSearchCtasPerSm;
     uint32_t vis_slots_override = 0; // IDB_VIS_SLOTS (tests): exact per-warp visited-table size, to force the overflow -> retry path
-    int vis_bitmap = 0;           // IDB_VIS_BITMAP: 0 hash set, 1 bitmap over PointIds when it is no bigger than 2x the hash table
+    int vis_bitmap = 1;           // IDB_VIS_BITMAP: 0 hash set, 1 bitmap over PointIds when it is no bigger than 2x the hash table
     int variant = 0;              // IDB_VARIANT: alternative (rows in flight, CTAs/SM) instantiations of K1
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -8,14 +8,8 @@ namespace idb {
 // ---------------------------------------------------------------------------------------------------------
 // K1: batched Hnsw::search — persistent grid, one warp per live query, queries claimed from an atomic counter.
 // ---------------------------------------------------------------------------------------------------------
-// LAND: each warp also owns a shared-memory landing zone of B rows, filled by cp.async, so that 2*B rows are in flight per
-// round trip of the row gathers (B in registers + B in shared memory); see batch_distances_impl.
-template <int CH, int B, class RT, bool LAND>
-constexpr int land_bytes() { return LAND ? B * CH * 32 * (int)RT::kChunkBytes : 0; }
-template <int CH, int EF_T, int B, class RT, bool LAND>
-constexpr int search_warp_bytes() { return 2 * 32 * EF_T * 8 + kSmallVisSlots * 4 + 128 * 4 + 128 * 8 + land_bytes<CH, B, RT, LAND>(); }
-
-template <int CH, int ROW_T, int EF_T, int B, int OCC, class RT = RowF32, bool LAND = false, bool SPEC = false>
+// PIPE: work ahead on the predicted next candidate during the distance trips (hnsw_device.cuh NextSpec; bitmap visited tier).
+template <int CH, int ROW_T, int EF_T, int B, int OCC, class RT = RowF32, bool PIPE = false>
 __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -23,7 +17,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchAr
     const uint32_t gwarp = blockIdx.x * kSearchWarps + warp;
 
     constexpr int kNearBytes = 2 * 32 * EF_T * 8;
-    constexpr int kWarpBytes = search_warp_bytes<CH, EF_T, B, RT, LAND>();
+    constexpr int kWarpBytes = kNearBytes + kSmallVisSlots * 4 + 128 * 4 + 128 * 8;
     unsigned char* base = smem_raw + (size_t)warp * kWarpBytes;
 
     WarpState s;
@@ -32,7 +26,6 @@ __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchAr
     s.vis.small = reinterpret_cast<uint32_t*>(base + kNearBytes);
     s.cpid = s.vis.small + kSmallVisSlots;
     s.ckey = reinterpret_cast<uint64_t*>(s.cpid + 128);
-    s.land = LAND ? reinterpret_cast<unsigned char*>(s.ckey + 128) : nullptr;
     s.vis.big = a.vis_tables + (size_t)gwarp * a.vis_stride;
     s.vis.gslots = a.gslots;
     s.vis.gshift = a.gshift;
@@ -58,7 +51,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchAr
             q[j] = c < a.g.nchunks ? __ldg(qrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 
-        descend<CH, ROW_T, EF_T, B, false, RT, LAND, SPEC>(a.g, s, q, 0u, a.ef, lane, a.counters ? a.counters + qi * 4 : nullptr);
+        descend<CH, ROW_T, EF_T, B, false, RT, PIPE>(a.g, s, q, 0u, a.ef, lane, a.counters ? a.counters + qi * 4 : nullptr);
 
         const bool ok = s.status == kQueryOk;
         const uint64_t* near = (s.near_base + s.cur * s.near_len);
@@ -82,37 +75,35 @@ __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchAr
     }
 }
 
-template <int CH, int ROW_T, int EF_T, int B, int OCC = kSearchCtasPerSm, class RT = RowF32, bool LAND = false, bool SPEC = false>
+template <int CH, int ROW_T, int EF_T, int B, int OCC = kSearchCtasPerSm, class RT = RowF32, bool PIPE = false>
 static cudaError_t launch_search(const SearchArgs& a, int grid, cudaStream_t stream) {
-    constexpr int kWarpBytes = search_warp_bytes<CH, EF_T, B, RT, LAND>();
-    static_assert(kWarpBytes % 16 == 0, "per-warp shared-memory block must keep 16-byte alignment");
+    constexpr int kWarpBytes = 2 * 32 * EF_T * 8 + kSmallVisSlots * 4 + 128 * 4 + 128 * 8;
     const int smem = kWarpBytes * kSearchWarps;
-    static_assert((kWarpBytes * kSearchWarps + 1024) * OCC <= 228 * 1024, "OCC CTAs of this variant do not fit one SM's shared memory");
-    auto kern = search_kernel<CH, ROW_T, EF_T, B, OCC, RT, LAND, SPEC>;
+    auto kern = search_kernel<CH, ROW_T, EF_T, B, OCC, RT, PIPE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kSearchWarps * 32, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
+// PIPE costs ~8 live registers across the distance trips: with 8 chunks per lane (dim > 768) the query alone takes 32 and the
+// PIPE kernels spill, so those shapes keep the plain loop.
+template <int CH, int ROW_T, int EF_T, int B, class RT>
+cudaError_t launch_search_pipe(const SearchArgs& a, bool pipe, int grid, cudaStream_t st) {
+    if constexpr (CH <= 6) {
+        if (pipe) return launch_search<CH, ROW_T, EF_T, B, kSearchCtasPerSm, RT, true>(a, grid, st);
+    }
+    return launch_search<CH, ROW_T, EF_T, B, kSearchCtasPerSm, RT, false>(a, grid, st);
+}
 template <int CH, int B, class RT>
 cudaError_t dispatch_row_ef_rt(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st) {
-    // ef <= 128: the per-warp state is small enough that an extra B-row landing zone per warp still fits 16 warps per SM
-    const bool land = a.variant == kVariantLand, spec = a.variant == kVariantLandSpec;
+    const bool pipe = a.vis_bitmap && a.variant != kVariantNoPipe;  // working ahead needs the bitmap visited tier
     if (row_t <= 2) {
-        if (ef_t <= 4) {
-            if (spec) return launch_search<CH, 2, 4, B, kSearchCtasPerSm, RT, true, true>(a, grid, st);
-            return land ? launch_search<CH, 2, 4, B, kSearchCtasPerSm, RT, true>(a, grid, st)
-                        : launch_search<CH, 2, 4, B, kSearchCtasPerSm, RT, false>(a, grid, st);
-        }
-        return launch_search<CH, 2, 16, B, kSearchCtasPerSm, RT>(a, grid, st);
+        if (ef_t <= 4) return launch_search_pipe<CH, 2, 4, B, RT>(a, pipe, grid, st);
+        return launch_search_pipe<CH, 2, 16, B, RT>(a, pipe, grid, st);
     }
-    if (ef_t <= 4) {
-        if (spec) return launch_search<CH, 4, 4, B, kSearchCtasPerSm, RT, true, true>(a, grid, st);
-        return land ? launch_search<CH, 4, 4, B, kSearchCtasPerSm, RT, true>(a, grid, st)
-                    : launch_search<CH, 4, 4, B, kSearchCtasPerSm, RT, false>(a, grid, st);
-    }
-    return launch_search<CH, 4, 16, B, kSearchCtasPerSm, RT>(a, grid, st);
+    if (ef_t <= 4) return launch_search_pipe<CH, 4, 4, B, RT>(a, pipe, grid, st);
+    return launch_search_pipe<CH, 4, 16, B, RT>(a, pipe, grid, st);
 }
 template <int CH, int B>
 cudaError_t dispatch_row_ef(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st) {
