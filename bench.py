@@ -32,8 +32,14 @@ sys.path.insert(0, os.path.join(ROOT, "instant-distance_b200", "python"))
 from tests import datagen  # noqa: E402  (seeded synthetic data shared with the tests)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE K1 launch at the headline config, from the committed ncu capture
-NCU_TRAFFIC_BYTES = 25.925532e9 + 3.235579e9
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE K1 launch at the headline config, from the committed ncu --set full
+    capture of the current kernel (profiles/k1_ncu_traffic.json names the capture it was read from)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "k1_ncu_traffic.json")))
+        return float(d["dram_bytes_per_launch"]), d["source"]
+    except Exception:  # noqa: BLE001
+        return None, None
 
 
 def log(*a):
@@ -448,8 +454,8 @@ def main():
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * args.dim * 4,
                     "d2h_bytes_per_step": nq * k * 8 + nq * 4},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC_BYTES if args.n == 1_000_000 and args.dim == 128 and args.batch == 10_000 else None,
-                         "traffic_source": "profiles/r01_call6_search_kernel_1M.md (ncu --set full: dram read + write bytes of one launch)",
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic()[0] if args.n == 1_000_000 and args.dim == 128 and args.batch == 10_000 else None,
+                         "traffic_source": ncu_traffic()[1],
                          "kernel": "search_kernel (K1 search_layer)", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": float(np.mean(alg_bytes)), "peak_source": peak_src},
             "cpu_baseline": cpu, "clocks": clocks,

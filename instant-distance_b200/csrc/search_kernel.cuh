@@ -97,7 +97,7 @@ cudaError_t launch_search_pipe(const SearchArgs& a, bool pipe, int grid, cudaStr
 }
 template <int CH, int B, class RT>
 cudaError_t dispatch_row_ef_rt(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st) {
-    const bool pipe = a.vis_bitmap && a.variant != kVariantNoPipe;  // working ahead needs the bitmap visited tier
+    const bool pipe = a.vis_bitmap && a.variant == kVariantPipe;  // working ahead needs the bitmap visited tier (measured -2 %: off)
     if (row_t <= 2) {
         if (ef_t <= 4) return launch_search_pipe<CH, 2, 4, B, RT>(a, pipe, grid, st);
         return launch_search_pipe<CH, 2, 16, B, RT>(a, pipe, grid, st);
