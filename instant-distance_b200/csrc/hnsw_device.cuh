@@ -52,18 +52,36 @@ struct GraphView {
 //   lane l owns float4 chunks l, l+32, l+64, ...; four fmaf chains (one per float4 component);
 //   lane sum (a0+a1)+(a2+a3); xor butterfly over lanes with offsets 1, 2, 4, 8, 16.
 // ---------------------------------------------------------------------------------------------------------
+// sm_100 packed fp32: one FADD2 / FFMA2 does two independent IEEE round-to-nearest operations (same results as the scalar
+// instructions, half the issue slots).  A float4 chunk sits in an aligned register quad, so (x,y) and (z,w) are register pairs.
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t f32x2_sub(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
 template <int CH>
 __device__ __forceinline__ float lane_partial(const float4 (&q)[CH], const float4 (&v)[CH]) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    uint64_t a01 = 0ull, a23 = 0ull;  // (+0, +0): the four fmaf chains a0..a3 of the canonical order, two per register pair
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
-        float d0 = __fsub_rn(q[j].x, v[j].x), d1 = __fsub_rn(q[j].y, v[j].y);
-        float d2 = __fsub_rn(q[j].z, v[j].z), d3 = __fsub_rn(q[j].w, v[j].w);
-        a0 = __fmaf_rn(d0, d0, a0);
-        a1 = __fmaf_rn(d1, d1, a1);
-        a2 = __fmaf_rn(d2, d2, a2);
-        a3 = __fmaf_rn(d3, d3, a3);
+        const uint64_t d01 = f32x2_sub(f32x2_pack(q[j].x, q[j].y), f32x2_pack(v[j].x, v[j].y));
+        const uint64_t d23 = f32x2_sub(f32x2_pack(q[j].z, q[j].w), f32x2_pack(v[j].z, v[j].w));
+        a01 = f32x2_fma(d01, d01, a01);
+        a23 = f32x2_fma(d23, d23, a23);
     }
+    float a0, a1, a2, a3;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a01));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a2), "=f"(a3) : "l"(a23));
     return __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
 }
 
@@ -300,16 +318,14 @@ __device__ __forceinline__ uint32_t lower_bound_keys(const uint64_t* a, uint32_t
 // Distances from q to the n_new points listed in cpid (shared, 16-byte aligned), NB rows in flight per lane; writes the
 // keys (canonical distance bits << 32 | pid) to ckey.  The only place in the traversal that touches point rows.
 // kFull: every lane owns a real chunk in every one of its CH slots (dim is a multiple of 128) -> no chunk predicates.
-// `hook(trip)` runs once per trip right after that trip's row loads have been issued (its own memory operations then
-// overlap them); search_layer uses it to work ahead on the predicted next candidate (NextSpec below).
-struct NoTripHook {
-    __device__ __forceinline__ void operator()(uint32_t) const {}
-};
-template <int CH, int NB, bool kFull, class RT, class Hook>
+template <int CH, int NB, bool kFull, class RT>
 __device__ __forceinline__ void batch_distances_impl(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid,
-                                                     uint64_t* ckey, uint32_t n_new, int lane, Hook& hook) {
+                                                     uint64_t* ckey, uint32_t n_new, int lane) {
     const uint32_t row_bytes = g.nchunks * RT::kChunkBytes;
     const char* lane_base = g.points + lane * RT::kChunkBytes;
+    // keep the lane's base address in a register pair: each row address is then ONE IMAD.WIDE (pid * row_bytes + base)
+    // instead of IMAD.WIDE + a 64-bit add of the kernel-parameter base
+    asm volatile("" : "+l"(lane_base));
     if (g.flags & kOptPrefetchVectors) {  // pull every row of this expansion into L2 now; the batches below then hit L2
         const uint32_t lines = (row_bytes + 127) / 128;  // 128-byte lines per row
         for (uint32_t ln = 0; ln < lines; ++ln)
@@ -323,16 +339,24 @@ __device__ __forceinline__ void batch_distances_impl(const GraphView& g, const f
     for (uint32_t b0 = 0; b0 < n_new; b0 += NB) {
         const uint32_t nb = n_new - b0;  // rows in this batch (uniform); entries i >= nb are predicated off
         typename RT::Raw v[NB][CH];
+        if (kFull && nb >= (uint32_t)NB) {  // uniform; two of the ~three trips per expansion: plain loads, no predicates, no zero fill
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {
-            // branch-free on purpose: `if (i < nb) {load; use}` makes ptxas emit two branches per row
-            const bool ok = (uint32_t)i < nb;
-            const char* row = lane_base + (size_t)cpid[b0 + i] * row_bytes;  // shared-memory broadcast of the id
+            for (int i = 0; i < NB; ++i) {
+                const char* row = lane_base + (size_t)cpid[b0 + i] * row_bytes;  // shared-memory broadcast of the id
 #pragma unroll
-            for (int j = 0; j < CH; ++j)
-                v[i][j] = (ok && cok[j]) ? RT::ld_raw(row + j * 32 * RT::kChunkBytes) : RT::zero();
+                for (int j = 0; j < CH; ++j) v[i][j] = RT::ld_raw(row + j * 32 * RT::kChunkBytes);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                // branch-free on purpose: `if (i < nb) {load; use}` makes ptxas emit two branches per row
+                const bool ok = (uint32_t)i < nb;
+                const char* row = lane_base + (size_t)cpid[b0 + i] * row_bytes;  // shared-memory broadcast of the id
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                    v[i][j] = (ok && cok[j]) ? RT::ld_raw(row + j * 32 * RT::kChunkBytes) : RT::zero();
+            }
         }
-        hook(b0 / NB);
         float p[NB];
 #pragma unroll
         for (int i = 0; i < NB; ++i) p[i] = lane_partial_raw<CH, RT>(q, v[i]);
@@ -341,93 +365,11 @@ __device__ __forceinline__ void batch_distances_impl(const GraphView& g, const f
     }
     __syncwarp();
 }
-template <int CH, int NB, class RT, class Hook>
-__device__ __forceinline__ void batch_distances(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid, uint64_t* ckey,
-                                                uint32_t n_new, int lane, Hook& hook) {
-    // (a second, predicate-free instantiation for dim % 128 == 0 was tried: the two inlined copies made ptxas spill)
-    batch_distances_impl<CH, NB, false, RT, Hook>(g, q, cpid, ckey, n_new, lane, hook);
-}
-template <int CH, int NB, class RT = RowF32>
+template <int CH, int NB, class RT = RowF32, bool FULL = false>
 __device__ __forceinline__ void batch_distances(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid, uint64_t* ckey,
                                                 uint32_t n_new, int lane) {
-    NoTripHook none;
-    batch_distances_impl<CH, NB, false, RT, NoTripHook>(g, q, cpid, ckey, n_new, lane, none);
+    batch_distances_impl<CH, NB, FULL, RT>(g, q, cpid, ckey, n_new, lane);
 }
-
-// ---------------------------------------------------------------------------------------------------------
-// Working ahead on the NEXT candidate (PIPE variants of search_layer; bitmap visited tier only).
-// The candidate popped next is, ~80 % of the time, the second unexpanded entry of `nearest` as it stood at the current pop
-// (it changes only if this expansion admits something closer).  So while the distance trips of the current expansion are
-// in flight the warp (1) loads that entry's adjacency row and, one trip later, (2) issues the visited test-and-set of its
-// row entries.  Both round trips then overlap the row gathers instead of following them.  This is exact:
-//   * the speculative test-and-sets are issued after the current expansion's own ones have settled, i.e. in the order the
-//     sequential algorithm would perform them if the prediction holds;
-//   * if another candidate is popped instead, exactly the bits this speculation cleared are set again (atomicOr) before
-//     any other visited operation; nothing else reads the per-warp bitmap in between;
-//   * on leaving the layer an unconsumed speculation is rolled back the same way.
-// ---------------------------------------------------------------------------------------------------------
-template <int ROW_T>
-struct NextSpec {
-    uint32_t want;           // PointId to work ahead on during the coming trips; kInvalid = none
-    uint32_t pid;            // PointId whose row is held in ent[]; kInvalid = none
-    uint32_t ent[ROW_T];     // this lane's entries of that row
-    uint32_t old[ROW_T];     // results of the speculative visited test-and-sets (valid iff probed)
-    uint32_t count;          // NearestIter length of that row (valid iff probed)
-    bool probed;
-};
-template <int ROW_T>
-__device__ __forceinline__ uint32_t row_count(const uint32_t (&ent)[ROW_T]) {  // first INVALID (types.rs:178-191)
-    uint32_t count = 32 * ROW_T;
-#pragma unroll
-    for (int t = ROW_T - 1; t >= 0; --t) {
-        uint32_t m = __ballot_sync(kFullMask, ent[t] == kInvalid);
-        if (m) count = 32 * t + __ffs(m) - 1;
-    }
-    return count;
-}
-template <int ROW_T>
-__device__ __forceinline__ void spec_rollback(NextSpec<ROW_T>& sp, VisitedSet& vis, int lane) {
-    if (sp.pid != kInvalid && sp.probed) {
-#pragma unroll
-        for (int t = 0; t < ROW_T; ++t)
-            if ((uint32_t)(lane + 32 * t) < sp.count && ((sp.old[t] >> (sp.ent[t] & 31)) & 1u))
-                atomicOr(vis.big + (sp.ent[t] >> 5), 1u << (sp.ent[t] & 31));
-        __syncwarp();  // orders these before the test-and-sets other lanes issue next (same words are likely)
-    }
-    sp.pid = kInvalid;
-    sp.probed = false;
-}
-template <int ROW_T>
-struct SpecTripHook {
-    NextSpec<ROW_T>& sp;
-    VisitedSet& vis;
-    const uint32_t* rows;
-    uint32_t width, links;
-    int lane;
-    __device__ __forceinline__ void operator()(uint32_t trip) {
-        if (sp.want == kInvalid) return;
-        if (trip == 0) {
-            const uint32_t* row = rows + (size_t)sp.want * width;
-#pragma unroll
-            for (int t = 0; t < ROW_T; ++t) {
-                const uint32_t e = lane + 32 * t;
-                sp.ent[t] = kInvalid;
-                if (e < links) sp.ent[t] = __ldg(row + e);
-            }
-            sp.pid = sp.want;
-            sp.probed = false;
-        } else if (trip == 1) {
-            sp.count = row_count<ROW_T>(sp.ent);
-#pragma unroll
-            for (int t = 0; t < ROW_T; ++t) {
-                sp.old[t] = 0u;
-                if ((uint32_t)(lane + 32 * t) < sp.count) sp.old[t] = vis_bitmap_fetch_clear(vis.big, sp.ent[t]);
-            }
-            sp.probed = true;
-        }
-    }
-};
-
 
 // Rare path: something was evicted while its distance equals the new furthest distance.  Such an entry stays a
 // live candidate in the reference (strict `>` at lib.rs:601) iff it is unexpanded and had been ADMITTED
@@ -512,25 +454,16 @@ __device__ __forceinline__ uint64_t pop_min_tie(WarpState& s, int lane) {
 // kLive: rows may be rewritten concurrently (GPU build) -> read them through L2 (ld.global.cg), not the
 // read-only/L1 path.
 // ---------------------------------------------------------------------------------------------------------
-template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT, bool PIPE>
+template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT, bool FULL>
 __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, const float4 (&q)[CH], const uint32_t* rows,
                                              uint32_t width, uint32_t links, uint32_t ef_cur, bool seed_entry, int lane) {
     const uint32_t lt_mask = (1u << lane) - 1;
-    NextSpec<ROW_T> sp;
-    sp.want = kInvalid;
-    sp.pid = kInvalid;
-    sp.probed = false;
-    sp.count = 0;
-#pragma unroll
-    for (int t = 0; t < ROW_T; ++t) sp.ent[t] = kInvalid, sp.old[t] = 0u;
-    SpecTripHook<ROW_T> spec_hook{sp, s.vis, rows, width, links, lane};
     for (;;) {
         uint64_t* near = (s.near_base + s.cur * s.near_len);
         uint32_t n_new = 0;
         if (seed_entry) {
             // push(PointId(0)) (lib.rs:364 / 444): the entry point is the only "row entry" of a pseudo expansion
             seed_entry = false;
-            sp.want = kInvalid;
             vis_insert(s.vis, 0u, lane == 0);
             s.vis.count = 1;
             if (lane == 0) s.cpid[0] = 0u;
@@ -570,44 +503,29 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
                 break;  // heap empty, or its min is strictly beyond the furthest result (lib.rs:601-603)
             }
             s.n_expand++;
-            // work ahead on the second unexpanded entry (the likely next candidate) during this expansion's trips
-            sp.want = (PIPE && !kLive && s.vis.use_big && s.vis.bitmap && nxt >= 0) ? key_pid(near[nxt]) : kInvalid;
-            bool hit = false;
-            if constexpr (PIPE) {
-                hit = sp.pid == cpid;            // uniform
-                if (!hit) spec_rollback(sp, s.vis, lane);
-            }
 
             // ---- row of the candidate: NearestIter stops at the first INVALID (types.rs:178-191) ----------
             uint32_t ent[ROW_T];
-            if (PIPE && hit) {
+            const uint32_t* row = rows + (size_t)cpid * width;
 #pragma unroll
-                for (int t = 0; t < ROW_T; ++t) ent[t] = sp.ent[t];
-            } else {
-                const uint32_t* row = rows + (size_t)cpid * width;
-#pragma unroll
-                for (int t = 0; t < ROW_T; ++t) {
-                    uint32_t e = lane + 32 * t;
-                    ent[t] = kInvalid;
-                    if (e < links) ent[t] = kLive ? __ldcg(row + e) : __ldg(row + e);
-                }
+            for (int t = 0; t < ROW_T; ++t) {
+                uint32_t e = lane + 32 * t;
+                ent[t] = kInvalid;
+                if (e < links) ent[t] = kLive ? __ldcg(row + e) : __ldg(row + e);
             }
-            const bool pre = PIPE && hit && sp.probed;  // its visited test-and-sets are already done (or in flight)
-            const uint32_t count = pre ? sp.count : row_count<ROW_T>(ent);
-            sp.pid = kInvalid;
-            sp.probed = false;
+            uint32_t count = 32 * ROW_T;
+#pragma unroll
+            for (int t = ROW_T - 1; t >= 0; --t) {
+                uint32_t m = __ballot_sync(kFullMask, ent[t] == kInvalid);
+                if (m) count = 32 * t + __ffs(m) - 1;
+            }
             if (count == 0) continue;
 
             // ---- visited.insert for every row entry (lib.rs:705), compacted in row order ------------------
             if (!vis_reserve(s.vis, count, lane)) { s.status = kQueryVisitedOverflow; break; }
             VisProbe probe[ROW_T];
-            if (pre) {
 #pragma unroll
-                for (int t = 0; t < ROW_T; ++t) probe[t].old = sp.old[t], probe[t].h = ent[t] >> 5;
-            } else {
-#pragma unroll
-                for (int t = 0; t < ROW_T; ++t) probe[t] = vis_probe(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count);
-            }
+            for (int t = 0; t < ROW_T; ++t) probe[t] = vis_probe(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count);
 #pragma unroll
             for (int t = 0; t < ROW_T; ++t) {
                 const bool fresh = vis_settle(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count, probe[t]);
@@ -622,8 +540,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
         }
 
         // ---- distances (lib.rs:709-710) --------------------------------------------------------------------
-        if constexpr (PIPE) batch_distances<CH, B, RT>(g, q, s.cpid, s.ckey, n_new, lane, spec_hook);
-        else batch_distances<CH, B, RT>(g, q, s.cpid, s.ckey, n_new, lane);
+        batch_distances<CH, B, RT, FULL>(g, q, s.cpid, s.ckey, n_new, lane);
         uint64_t keyg[ROW_T];
 #pragma unroll
         for (int gi = 0; gi < ROW_T; ++gi) {
@@ -720,7 +637,6 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
             if (s.status != kQueryOk) break;
         }
     }
-    if constexpr (PIPE) spec_rollback(sp, s.vis, lane);  // an unconsumed speculation leaves the visited set exact
 }
 
 // Search::cull (lib.rs:729-737): candidates := nearest; visited := {pids of nearest}.
@@ -745,7 +661,7 @@ __device__ __forceinline__ void cull(WarpState& s, int lane, bool next_big) {
 // Construction::insert's descent (lib.rs:443-463) when target_layer = the insert layer, ef_target = ef_construction.
 // Layers above the target are searched on the UpperNode snapshots with ef = 1; the target layer on the zero table.
 // On return nearest = (s.near_base + s.cur * s.near_len)[0..s.cnt).  counters (if non-null): {n_expand_upper, n_dist_upper, n_expand_target, n_dist_target}.
-template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT = RowF32, bool PIPE = false>
+template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT = RowF32, bool FULL = false>
 __device__ __forceinline__ void descend(const GraphView& g, WarpState& s, const float4 (&q)[CH], uint32_t target_layer,
                                         uint32_t ef_target, int lane, uint32_t* counters4) {
     s.cur = 0;
@@ -764,7 +680,7 @@ __device__ __forceinline__ void descend(const GraphView& g, WarpState& s, const 
         const uint32_t* rows = above ? g.upper[cur - 1] : g.zero;
         const uint32_t width = above ? g.M : 2 * g.M;
         const uint32_t links = (above || target_layer != 0) ? g.M : 2 * g.M;  // lib.rs:445 / 366-369
-        search_layer<CH, ROW_T, EF_T, B, kLive, RT, PIPE>(g, s, q, rows, width, links, above ? 1u : ef_target, seed, lane);
+        search_layer<CH, ROW_T, EF_T, B, kLive, RT, FULL>(g, s, q, rows, width, links, above ? 1u : ef_target, seed, lane);
         seed = false;
         if (!above || s.status != kQueryOk) break;
         cull<EF_T>(s, lane, /*next_big=*/(cur - 1 == target_layer));

@@ -15,7 +15,6 @@ namespace idb {
 constexpr int kSearchWarps = 4;        // warps (= live queries) per CTA
 constexpr int kSearchCtasPerSm = 4;    // resident CTAs per SM -> 16 live queries per SM, <= 128 registers per thread
 constexpr int kMaxCtasPerSm = 8;       // upper bound over the tuning variants (scratch is sized for it)
-constexpr int kVariantPipe = 8;       // IDB_VARIANT: K1 working ahead on the predicted next candidate (hnsw_device.cuh NextSpec)
 constexpr int kRetryWarps = 32;        // warps of the (normally idle) overflow-retry pass
 constexpr uint32_t kRetrySlots = 1u << 21;
 

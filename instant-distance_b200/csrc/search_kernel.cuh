@@ -8,8 +8,9 @@ namespace idb {
 // ---------------------------------------------------------------------------------------------------------
 // K1: batched Hnsw::search — persistent grid, one warp per live query, queries claimed from an atomic counter.
 // ---------------------------------------------------------------------------------------------------------
-// PIPE: work ahead on the predicted next candidate during the distance trips (hnsw_device.cuh NextSpec; bitmap visited tier).
-template <int CH, int ROW_T, int EF_T, int B, int OCC, class RT = RowF32, bool PIPE = false>
+// FULL: dim is a multiple of 128, i.e. every lane owns a real chunk in each of its CH slots: no chunk predicates, and
+// full batches of row loads carry no predicates at all (hnsw_device.cuh batch_distances_impl).
+template <int CH, int ROW_T, int EF_T, int B, int OCC, class RT = RowF32, bool FULL = false>
 __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchAr
             q[j] = c < a.g.nchunks ? __ldg(qrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 
-        descend<CH, ROW_T, EF_T, B, false, RT, PIPE>(a.g, s, q, 0u, a.ef, lane, a.counters ? a.counters + qi * 4 : nullptr);
+        descend<CH, ROW_T, EF_T, B, false, RT, FULL>(a.g, s, q, 0u, a.ef, lane, a.counters ? a.counters + qi * 4 : nullptr);
 
         const bool ok = s.status == kQueryOk;
         const uint64_t* near = (s.near_base + s.cur * s.near_len);
@@ -75,35 +76,30 @@ __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchAr
     }
 }
 
-template <int CH, int ROW_T, int EF_T, int B, int OCC = kSearchCtasPerSm, class RT = RowF32, bool PIPE = false>
+template <int CH, int ROW_T, int EF_T, int B, int OCC = kSearchCtasPerSm, class RT = RowF32, bool FULL = false>
 static cudaError_t launch_search(const SearchArgs& a, int grid, cudaStream_t stream) {
     constexpr int kWarpBytes = 2 * 32 * EF_T * 8 + kSmallVisSlots * 4 + 128 * 4 + 128 * 8;
     const int smem = kWarpBytes * kSearchWarps;
-    auto kern = search_kernel<CH, ROW_T, EF_T, B, OCC, RT, PIPE>;
+    auto kern = search_kernel<CH, ROW_T, EF_T, B, OCC, RT, FULL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kSearchWarps * 32, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
-// PIPE costs ~8 live registers across the distance trips: with 8 chunks per lane (dim > 768) the query alone takes 32 and the
-// PIPE kernels spill, so those shapes keep the plain loop.
 template <int CH, int ROW_T, int EF_T, int B, class RT>
-cudaError_t launch_search_pipe(const SearchArgs& a, bool pipe, int grid, cudaStream_t st) {
-    if constexpr (CH <= 6) {
-        if (pipe) return launch_search<CH, ROW_T, EF_T, B, kSearchCtasPerSm, RT, true>(a, grid, st);
-    }
+cudaError_t launch_search_full(const SearchArgs& a, int grid, cudaStream_t st) {
+    if (a.g.nchunks == 32u * CH) return launch_search<CH, ROW_T, EF_T, B, kSearchCtasPerSm, RT, true>(a, grid, st);
     return launch_search<CH, ROW_T, EF_T, B, kSearchCtasPerSm, RT, false>(a, grid, st);
 }
 template <int CH, int B, class RT>
 cudaError_t dispatch_row_ef_rt(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st) {
-    const bool pipe = a.vis_bitmap && a.variant == kVariantPipe;  // working ahead needs the bitmap visited tier (measured -2 %: off)
     if (row_t <= 2) {
-        if (ef_t <= 4) return launch_search_pipe<CH, 2, 4, B, RT>(a, pipe, grid, st);
-        return launch_search_pipe<CH, 2, 16, B, RT>(a, pipe, grid, st);
+        if (ef_t <= 4) return launch_search_full<CH, 2, 4, B, RT>(a, grid, st);
+        return launch_search_full<CH, 2, 16, B, RT>(a, grid, st);
     }
-    if (ef_t <= 4) return launch_search_pipe<CH, 4, 4, B, RT>(a, pipe, grid, st);
-    return launch_search_pipe<CH, 4, 16, B, RT>(a, pipe, grid, st);
+    if (ef_t <= 4) return launch_search_full<CH, 4, 4, B, RT>(a, grid, st);
+    return launch_search_full<CH, 4, 16, B, RT>(a, grid, st);
 }
 template <int CH, int B>
 cudaError_t dispatch_row_ef(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st) {
