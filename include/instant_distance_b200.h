@@ -146,6 +146,11 @@ IDB_API idb_status idb_index_last_kernel_ms(idb_index* index, float* out_ms, uin
  * (0 = all independent).  *out_bytes = bytes gathered per run. */
 IDB_API idb_status idb_debug_gather_bench(idb_index* index, uint32_t n_items, uint32_t batches, uint32_t chain, uint32_t reps,
                                           float* out_ms, double* out_bytes);
+/* Same with K1's second memory stream riding along: `atomics_per_batch` visited-style atomicAnd per 16-row batch on a per-warp
+ * n-bit bitmap that is wiped after every item.  mode 1: atomics overlap the row loads (traffic-mix ceiling); mode 2: the row loads
+ * wait for them (K1's dependency).  *out_bytes counts the ROW bytes only, like K1's algorithmic bytes. */
+IDB_API idb_status idb_debug_gather_mix_bench(idb_index* index, uint32_t n_items, uint32_t batches, uint32_t chain, uint32_t reps,
+                                              uint32_t atomics_per_batch, uint32_t mode, float* out_ms, double* out_bytes);
 
 IDB_API void* idb_index_stream(idb_index* index);      /* the cudaStream_t all work of this index is enqueued on */
 IDB_API idb_status idb_index_sync(idb_index* index);   /* cudaStreamSynchronize on it */

@@ -18,7 +18,7 @@ OK, ERR_INVALID_ARG, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_IO, ERR_FORMAT, ERR_CAPACI
 SYMBOLS = [
     "idb_params_default", "idb_build_f32", "idb_index_from_graph_f32", "idb_index_from_graph_bf16", "idb_search_batch_f32",
     "idb_search_batch_device", "idb_last_search_counters", "idb_index_info", "idb_index_export_points",
-    "idb_index_export_zero", "idb_index_export_upper", "idb_index_save", "idb_index_load", "idb_index_set_profiling", "idb_index_last_kernel_ms", "idb_debug_gather_bench",
+    "idb_index_export_zero", "idb_index_export_upper", "idb_index_save", "idb_index_load", "idb_index_set_profiling", "idb_index_last_kernel_ms", "idb_debug_gather_bench", "idb_debug_gather_mix_bench",
     "idb_index_stream", "idb_index_sync", "idb_index_free",
     "idb_comm_unique_id", "idb_comm_create", "idb_comm_free", "idb_index_set_id_map", "idb_sharded_search_batch_f32",
     "idb_sharded_search_batch_device", "idb_distance_f32", "idb_host_alloc", "idb_host_free", "idb_last_error", "idb_version", "idb_device_count",
@@ -75,6 +75,7 @@ def lib():
     L.idb_index_save.argtypes = [vp, C.c_char_p]
     L.idb_index_load.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(vp), u64p]
     L.idb_debug_gather_bench.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, f32p, C.POINTER(C.c_double)]
+    L.idb_debug_gather_mix_bench.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, f32p, C.POINTER(C.c_double)]
     L.idb_index_set_profiling.argtypes = [vp, C.c_int32]
     L.idb_index_last_kernel_ms.argtypes = [vp, f32p, u32p]
     L.idb_index_stream.argtypes = [vp]
@@ -257,6 +258,11 @@ class Index:
     def gather_bench(self, n_items=10000, batches=288, chain=0, reps=3):
         ms, by = C.c_float(), C.c_double()
         check(lib().idb_debug_gather_bench(self._h, n_items, batches, chain, reps, C.byref(ms), C.byref(by)))
+        return float(ms.value), float(by.value)
+
+    def gather_mix_bench(self, n_items=10000, batches=288, chain=0, reps=3, atomics=21, mode=1):
+        ms, by = C.c_float(), C.c_double()
+        check(lib().idb_debug_gather_mix_bench(self._h, n_items, batches, chain, reps, atomics, mode, C.byref(ms), C.byref(by)))
         return float(ms.value), float(by.value)
 
     def set_profiling(self, on=True):

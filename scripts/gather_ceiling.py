@@ -12,14 +12,20 @@ import numpy as np  # noqa: E402
 from instant_distance_b200 import _abi  # noqa: E402
 from tests import datagen  # noqa: E402
 
+MIX = "--mix" in sys.argv  # also measure with K1's visited-style atomic stream riding along (call 26)
 n = 1_000_000
 pts = datagen.sift_shaped(n, 128, 1)
 zero = np.full((n, 64), 0xFFFFFFFF, dtype=np.uint32)
-for ctas in ("4", "3", "2"):
+for ctas in (("4",) if MIX else ("4", "3", "2")):
     os.environ["IDB_CTAS_PER_SM"] = ctas
     ix = _abi.Index.from_graph(pts, zero, [], 32)
     for chain in (0, 6, 3, 1):
         ms, by = ix.gather_bench(n_items=10000, batches=288, chain=chain, reps=3)
         print(json.dumps({"ctas_per_sm": int(ctas), "warps_per_sm": int(ctas) * 4, "chain": chain, "ms": ms, "GBps": by / (ms / 1e3) / 1e9,
                           "frac_of_6572": by / (ms / 1e3) / 1e9 / 6572.5}), flush=True)
+    if MIX:
+        for mode, chain, atomics in ((1, 0, 21), (1, 3, 21), (2, 0, 21), (2, 3, 21), (1, 3, 0), (2, 3, 32)):
+            ms, by = ix.gather_mix_bench(n_items=10000, batches=288, chain=chain, reps=3, atomics=atomics, mode=mode)
+            print(json.dumps({"ctas_per_sm": int(ctas), "mix_mode": mode, "atomics_per_batch": atomics, "chain": chain, "ms": ms,
+                              "row_GBps": by / (ms / 1e3) / 1e9, "frac_of_6572": by / (ms / 1e3) / 1e9 / 6572.5}), flush=True)
     ix.close()
