@@ -136,25 +136,38 @@ idb_status Index::ensure_search_scratch(uint32_t ef, uint64_t nq, uint32_t k) {
         CUDA_TRY(fill_u32(sc.vis_tables, words, kInvalid, stream));
         sc.vis_stride = want_stride;
         sc.gslots = want_slots;
-        if (l2_persist) {
-            // Keep the per-warp visited tables resident in L2: point rows stream through once, the tables are hit
-            // ~64 times per expansion.  Persisting carve-out + access-policy window on this index's stream.
-            int max_persist = 0, max_window = 0;
-            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
-            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
-            const size_t bytes = words * 4;
-            const size_t carve = std::min<size_t>(bytes, (size_t)max_persist);
-            if (carve > 0 && max_window > 0) {
-                CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
-                cudaStreamAttrValue av;
-                std::memset(&av, 0, sizeof(av));
-                av.accessPolicyWindow.base_ptr = sc.vis_tables;
-                av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)max_window);
-                av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)av.accessPolicyWindow.num_bytes);
-                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                CUDA_TRY(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
+    // bucket-set flavour (K1's default when it fits): ~1.25 slots per id a query can possibly visit (2M per expansion, ~ef
+    // expansions), compact tables, kept in the persisting part of L2 by an access-policy window on this index's stream.
+    sc.bucket_slots = 0;
+    if (vis_buckets && !vis_slots_override) {
+        uint32_t slots = std::max<uint32_t>(1024u, next_pow2(((uint64_t)5 * 2 * M * std::max<uint32_t>(ef, 16u) + 3) / 4));
+        if (bucket_slots_override) slots = bucket_slots_override;  // tests: force the overflow -> retry path
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        const size_t bytes = (size_t)warps * slots * 4;
+        if (vis_buckets > 1 || (bytes <= (size_t)max_persist && bytes <= (size_t)max_window)) {
+            if (slots != sc.bucket_cap || !sc.bucket_tables) {
+                if (sc.bucket_tables) cudaFree(sc.bucket_tables);
+                sc.bucket_tables = nullptr;
+                CUDA_TRY(cudaMalloc(&sc.bucket_tables, bytes));
+                CUDA_TRY(fill_u32(sc.bucket_tables, (size_t)warps * slots, kInvalid, stream));
+                sc.bucket_cap = slots;
+                if (max_persist > 0 && max_window > 0) {
+                    const size_t carve = std::min<size_t>(bytes, (size_t)max_persist);
+                    CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+                    cudaStreamAttrValue av;
+                    std::memset(&av, 0, sizeof(av));
+                    av.accessPolicyWindow.base_ptr = sc.bucket_tables;
+                    av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)max_window);
+                    av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)av.accessPolicyWindow.num_bytes);
+                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    CUDA_TRY(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
+                }
             }
+            sc.bucket_slots = slots;
         }
     }
     if (!sc.retry_tables) {
@@ -197,11 +210,19 @@ idb_status Index::enqueue_search(const float* d_queries_padded, uint64_t nq, uin
     a.work_counter = reinterpret_cast<unsigned long long*>(sc.ctrl);
     a.fail_count = reinterpret_cast<uint32_t*>(sc.ctrl + 16);
     a.fail_list = sc.fail_list;
-    a.vis_tables = sc.vis_tables;
-    a.gslots = sc.bm_words ? sc.bm_words : sc.gslots;
-    a.gshift = 32 - (uint32_t)std::log2((double)sc.gslots);
-    a.vis_stride = sc.vis_stride;
-    a.vis_bitmap = sc.bm_words ? 1u : 0u;
+    if (sc.bucket_slots) {
+        a.vis_tables = sc.bucket_tables;
+        a.gslots = sc.bucket_slots;
+        a.gshift = 32 - (uint32_t)std::log2((double)sc.bucket_slots);
+        a.vis_stride = sc.bucket_slots;
+        a.vis_mode = kVisBuckets;
+    } else {
+        a.vis_tables = sc.vis_tables;
+        a.gslots = sc.bm_words ? sc.bm_words : sc.gslots;
+        a.gshift = 32 - (uint32_t)std::log2((double)sc.gslots);
+        a.vis_stride = sc.vis_stride;
+        a.vis_mode = sc.bm_words ? kVisBitmap : kVisHash;
+    }
     a.tie_tables = sc.tie_tables;
     a.variant = variant;
     a.out_keys = pending_out_keys;
@@ -233,7 +254,7 @@ idb_status Index::enqueue_search(const float* d_queries_padded, uint64_t nq, uin
     r.gslots = kRetrySlots;
     r.gshift = 32 - 21;
     r.vis_stride = kRetrySlots;
-    r.vis_bitmap = 0;
+    r.vis_mode = kVisHash;
     r.tie_tables = sc.tie_tables + (size_t)search_grid() * kSearchWarps * kTieCap;
     CUDA_TRY(dispatch_search(r, ch, row_t, ef_t, kRetryWarps / kSearchWarps, stream));
     last_nq = nq;
@@ -294,6 +315,7 @@ Index::~Index() {
     for (auto* p : d_upper) cudaFree(p);
     cudaFree(d_upper_ptrs);
     cudaFree(sc.vis_tables);
+    cudaFree(sc.bucket_tables);
     cudaFree(sc.retry_tables);
     cudaFree(sc.tie_tables);
     cudaFree(sc.ctrl);
@@ -335,6 +357,8 @@ idb_status Index::init_device(int dev) {
     if (const char* e = std::getenv("IDB_CTAS_PER_SM")) ctas_per_sm = std::min(kMaxCtasPerSm, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("IDB_VARIANT")) variant = std::atoi(e);
     if (const char* e = std::getenv("IDB_VIS_BITMAP")) vis_bitmap = std::atoi(e);
+    if (const char* e = std::getenv("IDB_VIS_BUCKETS")) vis_buckets = std::atoi(e);
+    if (const char* e = std::getenv("IDB_BUCKET_SLOTS")) bucket_slots_override = next_pow2((uint64_t)std::max(64, std::atoi(e)));
     if (const char* e = std::getenv("IDB_VIS_SLOTS")) vis_slots_override = next_pow2((uint64_t)std::max(64, std::atoi(e)));
     return IDB_OK;
 }

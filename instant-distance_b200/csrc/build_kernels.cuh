@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) insert_se
     s.vis.big = a.vis_tables + (size_t)gwarp * a.vis_stride;
     s.vis.gslots = a.gslots;
     s.vis.gshift = a.gshift;
-    s.vis.bitmap = false;
+    s.vis.mode = kVisHash;
     s.vis.count = 0;
     s.vis.use_big = false;
     s.ties = a.tie_tables + (size_t)gwarp * kTieCap;

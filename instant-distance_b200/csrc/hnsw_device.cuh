@@ -184,9 +184,17 @@ struct VisitedSet {
     uint32_t gshift;   // 32 - log2(gslots)
     uint32_t count;
     bool use_big;
-    bool bitmap;       // big tier is an (inverted) bitmap over PointIds instead of a hash set: bit SET = not visited, so a clean
-                       // table is all ones for both representations; gslots = words in use (a multiple of 4)
+    uint32_t mode;     // flavour of the big tier (VisMode).  A clean table is all ones (kInvalid) in every flavour;
+                       // gslots = words in use: hash slots (power of two) / bitmap words / bucket-set slots (power of two)
 };
+// Big-tier flavours, all exact:
+//   kVisHash    open addressing, one u32 slot per id, atomicCAS + linear probing (any n; used by the build and the retry pass)
+//   kVisBitmap  n bits, bit SET = not visited, one atomicAnd per id (n / 8 bytes per warp: DRAM resident)
+//   kVisBuckets 32-byte buckets of 8 ids, linear probing at bucket granularity.  ~1.25 slots per possible visited id, so the
+//               tables of all resident warps together fit the persisting part of L2 (K1's default when they do):
+//               a probe is ONE 32-byte read of an L2-resident sector instead of a read-modify-write of a random DRAM sector.
+enum VisMode : uint32_t { kVisHash = 0, kVisBitmap = 1, kVisBuckets = 2 };
+constexpr uint32_t kMaxBucketSteps = 16;  // buckets inspected per id before the query is handed to the retry pass
 
 __device__ __forceinline__ uint32_t vis_hash(uint32_t pid) { return pid * 0x9E3779B1u; }
 
@@ -215,8 +223,48 @@ __device__ __forceinline__ bool vis_insert_big(uint32_t* tab, uint32_t gshift, u
 __device__ __forceinline__ uint32_t vis_bitmap_fetch_clear(uint32_t* tab, uint32_t pid) {
     return atomicAnd(tab + (pid >> 5), ~(1u << (pid & 31)));
 }
+// ---- bucket set ------------------------------------------------------------------------------------------
+// Invariant (no deletions): an id lives in the first bucket, starting from its home bucket, that had a free slot when it was
+// inserted; so a lookup that finds a free slot in a bucket without having found the id knows the id is absent.
+struct Bucket8 { uint4 lo, hi; };
+__device__ __forceinline__ Bucket8 bucket_load(const uint32_t* tab, uint32_t b) {
+    const uint4* p = reinterpret_cast<const uint4*>(tab + (size_t)b * 8);
+    Bucket8 r;
+    r.lo = __ldcg(p);      // L2 (never L1: other lanes of this warp write these sectors)
+    r.hi = __ldcg(p + 1);
+    return r;
+}
+__device__ __forceinline__ uint32_t bucket_match(const Bucket8& k, uint32_t x) {  // bit i set <=> slot i == x
+    return (k.lo.x == x ? 1u : 0u) | (k.lo.y == x ? 2u : 0u) | (k.lo.z == x ? 4u : 0u) | (k.lo.w == x ? 8u : 0u) |
+           (k.hi.x == x ? 16u : 0u) | (k.hi.y == x ? 32u : 0u) | (k.hi.z == x ? 64u : 0u) | (k.hi.w == x ? 128u : 0u);
+}
+__device__ __forceinline__ uint32_t bucket_home(const VisitedSet& v, uint32_t pid) { return vis_hash(pid) >> (v.gshift + 3); }
+// Visited::insert for one id given the snapshot `k` of its home bucket.  Returns true iff the id was not in the set.
+// *overflow is set if no free slot was found within kMaxBucketSteps buckets.
+__device__ __forceinline__ bool bucket_resolve(VisitedSet& v, uint32_t pid, uint32_t b, Bucket8 k, bool* overflow) {
+    const uint32_t bmask = (v.gslots >> 3) - 1;
+    for (uint32_t step = 0;; ++step) {
+        if (bucket_match(k, pid)) return false;
+        uint32_t em = bucket_match(k, kInvalid);
+        while (em) {  // claim a free slot of the snapshot; another lane of this warp may have taken it in the meantime
+            const uint32_t i = __ffs(em) - 1;
+            em &= em - 1;
+            const uint32_t old = atomicCAS(v.big + (size_t)b * 8 + i, kInvalid, pid);
+            if (old == kInvalid) return true;
+            if (old == pid) return false;  // the same id twice in one row: the other lane inserted it
+        }
+        if (step + 1 >= kMaxBucketSteps) { *overflow = true; return false; }
+        b = (b + 1) & bmask;  // bucket full: the id, if present, is further along
+        k = bucket_load(v.big, b);
+    }
+}
 __device__ __forceinline__ bool vis_insert_big_any(VisitedSet& v, uint32_t pid) {
-    if (v.bitmap) return (vis_bitmap_fetch_clear(v.big, pid) >> (pid & 31)) & 1u;
+    if (v.mode == kVisBitmap) return (vis_bitmap_fetch_clear(v.big, pid) >> (pid & 31)) & 1u;
+    if (v.mode == kVisBuckets) {
+        bool ovf = false;  // (callers insert a handful of ids into a table sized for thousands: cannot overflow)
+        const uint32_t b = bucket_home(v, pid);
+        return bucket_resolve(v, pid, b, bucket_load(v.big, b), &ovf);
+    }
     return vis_insert_big(v.big, v.gshift, v.gslots - 1, pid);
 }
 
@@ -256,9 +304,14 @@ struct VisProbe { uint32_t old, h; };
 __device__ __forceinline__ VisProbe vis_probe(VisitedSet& v, uint32_t pid, bool want) {
     VisProbe r;
     r.old = 0u;
-    if (v.use_big && v.bitmap) {
+    if (v.use_big && v.mode == kVisBitmap) {
         r.h = pid >> 5;
         if (want) r.old = vis_bitmap_fetch_clear(v.big, pid);
+        return r;
+    }
+    if (v.use_big && v.mode == kVisBuckets) {  // (rows go through visited_row_buckets; this serves cull / the seed)
+        r.h = 0u;
+        if (want) r.old = vis_insert_big_any(v, pid) ? 1u : 0u;
         return r;
     }
     r.h = v.use_big ? (vis_hash(pid) >> v.gshift) : (vis_hash(pid) >> (32 - 9));
@@ -267,7 +320,8 @@ __device__ __forceinline__ VisProbe vis_probe(VisitedSet& v, uint32_t pid, bool 
 }
 __device__ __forceinline__ bool vis_settle(VisitedSet& v, uint32_t pid, bool want, VisProbe r) {
     if (!want) return false;
-    if (v.use_big && v.bitmap) return (r.old >> (pid & 31)) & 1u;
+    if (v.use_big && v.mode == kVisBitmap) return (r.old >> (pid & 31)) & 1u;
+    if (v.use_big && v.mode == kVisBuckets) return r.old != 0u;
     uint32_t* tab = v.use_big ? v.big : v.small;
     const uint32_t mask = v.use_big ? v.gslots - 1 : (uint32_t)(kSmallVisSlots - 1);
     uint32_t old = r.old, h = r.h;
@@ -285,7 +339,8 @@ __device__ __forceinline__ bool vis_insert(VisitedSet& v, uint32_t pid, bool wan
 // with kQueryVisitedOverflow and retried by the host with a larger table).
 __device__ __forceinline__ bool vis_reserve(VisitedSet& v, uint32_t incoming, int lane) {
     if (!v.use_big && v.count + incoming > kSmallVisSlots / 2) vis_migrate_to_big(v, lane);
-    if (v.use_big && !v.bitmap && v.count + incoming > (v.gslots / 4) * 3) return false;
+    if (v.use_big && v.mode == kVisHash && v.count + incoming > (v.gslots / 4) * 3) return false;
+    if (v.use_big && v.mode == kVisBuckets && v.count + incoming > (v.gslots / 8) * 7) return false;
     return true;
 }
 
@@ -523,15 +578,36 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
 
             // ---- visited.insert for every row entry (lib.rs:705), compacted in row order ------------------
             if (!vis_reserve(s.vis, count, lane)) { s.status = kQueryVisitedOverflow; break; }
-            VisProbe probe[ROW_T];
+            if (s.vis.use_big && s.vis.mode == kVisBuckets) {
+                // all home buckets of the row in flight at once (one 32-byte sector each), then resolve
+                Bucket8 bk[ROW_T];
+                uint32_t hb[ROW_T];
 #pragma unroll
-            for (int t = 0; t < ROW_T; ++t) probe[t] = vis_probe(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count);
+                for (int t = 0; t < ROW_T; ++t) {
+                    hb[t] = bucket_home(s.vis, ent[t]);
+                    if ((uint32_t)(lane + 32 * t) < count) bk[t] = bucket_load(s.vis.big, hb[t]);
+                }
+                bool ovf = false;
 #pragma unroll
-            for (int t = 0; t < ROW_T; ++t) {
-                const bool fresh = vis_settle(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count, probe[t]);
-                const uint32_t m = __ballot_sync(kFullMask, fresh);
-                if (fresh) s.cpid[n_new + __popc(m & lt_mask)] = ent[t];
-                n_new += __popc(m);
+                for (int t = 0; t < ROW_T; ++t) {
+                    bool fresh = false;
+                    if ((uint32_t)(lane + 32 * t) < count) fresh = bucket_resolve(s.vis, ent[t], hb[t], bk[t], &ovf);
+                    const uint32_t m = __ballot_sync(kFullMask, fresh);
+                    if (fresh) s.cpid[n_new + __popc(m & lt_mask)] = ent[t];
+                    n_new += __popc(m);
+                }
+                if (__any_sync(kFullMask, ovf)) { s.status = kQueryVisitedOverflow; break; }
+            } else {
+                VisProbe probe[ROW_T];
+#pragma unroll
+                for (int t = 0; t < ROW_T; ++t) probe[t] = vis_probe(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count);
+#pragma unroll
+                for (int t = 0; t < ROW_T; ++t) {
+                    const bool fresh = vis_settle(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count, probe[t]);
+                    const uint32_t m = __ballot_sync(kFullMask, fresh);
+                    if (fresh) s.cpid[n_new + __popc(m & lt_mask)] = ent[t];
+                    n_new += __popc(m);
+                }
             }
             s.vis.count += n_new;
             s.n_dist += n_new;

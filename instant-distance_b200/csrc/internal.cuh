@@ -45,9 +45,9 @@ struct SearchArgs {
     uint32_t* fail_count;
     uint32_t* fail_list;               // may be null (retry pass)
     uint32_t* vis_tables;
-    uint32_t gslots, gshift;           // hash flavour: slots (power of two) / 32 - log2(slots); bitmap flavour: words in use / unused
+    uint32_t gslots, gshift;           // words in use per warp / 32 - log2(gslots) (hash and bucket flavours: gslots is a power of two)
     uint32_t vis_stride;               // words between consecutive warps' tables (>= gslots)
-    uint32_t vis_bitmap;               // big visited tier is a bitmap over PointIds (hnsw_device.cuh VisitedSet::bitmap)
+    uint32_t vis_mode;                 // flavour of the big visited tier (hnsw_device.cuh VisMode)
     uint64_t* tie_tables;
     uint64_t* out_keys;                // optional: nq x k packed (distance bits << 32 | id_map[pid]) for the sharded all-gather
     const uint32_t* id_map;            // optional: PointId -> caller's global row id
@@ -57,7 +57,10 @@ struct SearchArgs {
 struct Scratch {
     uint32_t* vis_tables = nullptr;
     uint32_t gslots = 0;          // hash slots per warp (power of two)
-    uint32_t bm_words = 0;        // != 0: K1 uses the bitmap flavour with this many words per warp
+    uint32_t bm_words = 0;        // != 0: K1 may use the bitmap flavour with this many words per warp
+    uint32_t* bucket_tables = nullptr;  // bucket-set flavour: compact tables (bucket_slots words per warp) under a persisting-L2 window
+    uint32_t bucket_slots = 0;    // != 0: K1 uses the bucket-set flavour
+    uint32_t bucket_cap = 0;      // slots per warp the buffer was allocated for
     uint32_t vis_stride = 0;      // words per warp actually allocated (>= gslots; >= bitmap words when the bitmap flavour is on)
     uint32_t* retry_tables = nullptr;
     uint64_t* tie_tables = nullptr;
@@ -103,6 +106,8 @@ struct Index {
     int ctas_per_sm = kSearchCtasPerSm;
     uint32_t vis_slots_override = 0; // IDB_VIS_SLOTS (tests): exact per-warp visited-table size, to force the overflow -> retry path
     int vis_bitmap = 1;           // IDB_VIS_BITMAP: 0 hash set, 1 bitmap over PointIds when it is no bigger than 2x the hash table
+    uint32_t bucket_slots_override = 0; // IDB_BUCKET_SLOTS (tests): exact per-warp bucket-set size
+    int vis_buckets = 1;          // IDB_VIS_BUCKETS: 1 = bucket set when the tables of all resident warps fit the persisting part of L2
     int variant = 0;              // IDB_VARIANT: alternative (rows in flight, CTAs/SM) instantiations of K1
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

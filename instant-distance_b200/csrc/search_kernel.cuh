@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchAr
     s.vis.big = a.vis_tables + (size_t)gwarp * a.vis_stride;
     s.vis.gslots = a.gslots;
     s.vis.gshift = a.gshift;
-    s.vis.bitmap = a.vis_bitmap != 0;
+    s.vis.mode = a.vis_mode;
     s.vis.count = 0;
     s.vis.use_big = false;
     s.ties = a.tie_tables + (size_t)gwarp * kTieCap;

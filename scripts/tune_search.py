@@ -47,7 +47,7 @@ d_dist = torch.empty((args.batch, k), dtype=torch.float32, device="cuda")
 d_len = torch.empty((args.batch,), dtype=torch.int32, device="cuda")
 ref_ids = None
 results = []
-KNOBS = ["IDB_OPT", "IDB_VIS_MULT", "IDB_L2_PERSIST", "IDB_CTAS_PER_SM", "IDB_VARIANT", "IDB_VIS_BITMAP"]
+KNOBS = ["IDB_OPT", "IDB_VIS_MULT", "IDB_L2_PERSIST", "IDB_CTAS_PER_SM", "IDB_VARIANT", "IDB_VIS_BITMAP", "IDB_VIS_BUCKETS"]
 for cfg in args.configs.split(";"):
     for kname in KNOBS:
         os.environ.pop(kname, None)

@@ -218,3 +218,55 @@ def test_visited_overflow_goes_through_the_retry_pass(abi, oracle, monkeypatch):
     got = gpu.search(q, ef_search=100, k=10)
     assert (got[0] == want[0]).all() and got[1].tobytes() == want[1].tobytes() and (got[2] == want[2]).all()
     assert (gpu.last_counters(len(q)) == want[3]).all()
+
+
+FLAVOURS = {"buckets": {}, "bitmap": {"IDB_VIS_BUCKETS": "0"}, "hash": {"IDB_VIS_BUCKETS": "0", "IDB_VIS_BITMAP": "0"}}
+
+
+@pytest.mark.parametrize("flavour", sorted(FLAVOURS))
+def test_search_parity_every_visited_flavour(abi, oracle, monkeypatch, flavour):
+    """The wide-layer visited set has three exact flavours (bucket set in L2 / bitmap / hash set); all must give the oracle's answer."""
+    for k_, v_ in FLAVOURS[flavour].items():
+        monkeypatch.setenv(k_, v_)
+    for n, dim, M, ef, seed in [(5000, 128, 32, 100, 1), (3000, 16, 64, 200, 2), (4000, 300, 24, 100, 3)]:
+        pts = datagen.uniform(n, dim, 900 + seed)
+        ix, _ = oracle.build(pts, seed=seed, M=M, threads=4)
+        _check(abi, oracle, ix.export(), ix, datagen.uniform(300, dim, 17), ef)
+    pts = datagen.grid_ties(3000, 3, 5, side=12)  # exact ties and duplicate vectors
+    ix, _ = oracle.build(pts, seed=2)
+    _check(abi, oracle, ix.export(), ix, datagen.grid_ties(300, 3, 6, side=12), 10)
+
+
+def test_bucket_set_overflow_goes_through_the_retry_pass(abi, oracle, monkeypatch):
+    """A bucket set that is too small for the ids a query visits hands the query to the retry pass (hash set, 2^21 slots)."""
+    pts = datagen.uniform(20_000, 16, 13)
+    ix, _ = oracle.build(pts, seed=3, threads=8)
+    g = ix.export()
+    q = datagen.uniform(300, 16, 14)
+    want = ix.search(q, ef_search=100, k=10, counters=True)
+    assert want[3][:, 3].max() > 1024
+    monkeypatch.setenv("IDB_BUCKET_SLOTS", "1024")
+    gpu = abi.Index.from_graph(g.points, g.zero, g.upper, g.M)
+    got = gpu.search(q, ef_search=100, k=10)
+    assert (got[0] == want[0]).all() and got[1].tobytes() == want[1].tobytes() and (got[2] == want[2]).all()
+    assert (gpu.last_counters(len(q)) == want[3]).all()
+
+
+@pytest.mark.parametrize("flavour", sorted(FLAVOURS))
+def test_rows_with_repeated_ids(abi, oracle, monkeypatch, flavour):
+    """An adopted graph may list a PointId twice in one row (the reference's Visited then skips the second, types.rs:32-40)."""
+    for k_, v_ in FLAVOURS[flavour].items():
+        monkeypatch.setenv(k_, v_)
+    pts = datagen.uniform(4000, 24, 5)
+    ix, _ = oracle.build(pts, seed=7, threads=4)
+    g = ix.export()
+    zero = g.zero.copy()
+    rng = np.random.default_rng(1)
+    for r in rng.choice(len(zero), 1500, replace=False):
+        cnt = int((zero[r] != 0xFFFFFFFF).sum())
+        if cnt >= 3:
+            i, j = rng.choice(cnt, 2, replace=False)
+            zero[r, j] = zero[r, i]
+    g2 = oracle.Graph(g.points, zero, g.upper, g.M, g.ef_search)
+    ix2 = oracle.from_graph(g2)
+    _check(abi, oracle, g2, ix2, datagen.uniform(400, 24, 6), 100)
