@@ -6,6 +6,7 @@
 #include "internal.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -119,6 +120,8 @@ cudaError_t ensure_u64(uint64_t*& p, size_t& cap, size_t need) { return ensure(p
 cudaError_t ensure_f32(float*& p, size_t& cap, size_t need) { return ensure(p, cap, need); }
 
 
+static std::atomic<int> g_persist_users{0};  // live indexes holding bucket tables (they share the device's persisting-L2 set-aside)
+
 idb_status Index::ensure_search_scratch(uint32_t ef, uint64_t nq, uint32_t k) {
     // visited tables: one per resident warp, sized for >= 2x the worst plausible number of visited ids (2M per expansion)
     uint32_t want_slots = std::max<uint32_t>(1024u, next_pow2((uint64_t)vis_mult * 2 * M * std::max<uint32_t>(ef, 16u)));
@@ -149,6 +152,7 @@ idb_status Index::ensure_search_scratch(uint32_t ef, uint64_t nq, uint32_t k) {
         const size_t bytes = (size_t)warps * slots * 4;
         if (vis_buckets > 1 || (bytes <= (size_t)max_persist && bytes <= (size_t)max_window)) {
             if (slots != sc.bucket_cap || !sc.bucket_tables) {
+                if (!sc.bucket_tables) g_persist_users.fetch_add(1);
                 if (sc.bucket_tables) cudaFree(sc.bucket_tables);
                 sc.bucket_tables = nullptr;
                 CUDA_TRY(cudaMalloc(&sc.bucket_tables, bytes));
@@ -315,6 +319,10 @@ Index::~Index() {
     for (auto* p : d_upper) cudaFree(p);
     cudaFree(d_upper_ptrs);
     cudaFree(sc.vis_tables);
+    if (sc.bucket_tables) {  // hand the persisting lines back; the last user also returns the L2 set-aside
+        cudaCtxResetPersistingL2Cache();
+        if (g_persist_users.fetch_sub(1) == 1) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    }
     cudaFree(sc.bucket_tables);
     cudaFree(sc.retry_tables);
     cudaFree(sc.tie_tables);
