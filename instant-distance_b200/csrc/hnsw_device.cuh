@@ -194,7 +194,7 @@ struct VisitedSet {
 //               tables of all resident warps together fit the persisting part of L2 (K1's default when they do):
 //               a probe is ONE 32-byte read of an L2-resident sector instead of a read-modify-write of a random DRAM sector.
 enum VisMode : uint32_t { kVisHash = 0, kVisBitmap = 1, kVisBuckets = 2 };
-constexpr uint32_t kMaxBucketSteps = 16;  // buckets inspected per id before the query is handed to the retry pass
+constexpr uint32_t kMaxBucketSteps = 128;  // buckets inspected per id before the query is handed to the retry pass (load <= 7/8: never in practice)
 
 __device__ __forceinline__ uint32_t vis_hash(uint32_t pid) { return pid * 0x9E3779B1u; }
 
@@ -587,11 +587,27 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
                     hb[t] = bucket_home(s.vis, ent[t]);
                     if ((uint32_t)(lane + 32 * t) < count) bk[t] = bucket_load(s.vis.big, hb[t]);
                 }
+                // common case per id: not in its home bucket and the bucket has a free slot -> claim it.  The claims of all of a
+                // lane's ids are issued before any result is looked at (one L2 round trip for the row, not one per id).
+                uint32_t claim[ROW_T];   // result of the slot claim
+                uint32_t state[ROW_T];   // 0 visited / not a row entry, 1 claim in flight, 2 general path (full bucket)
+#pragma unroll
+                for (int t = 0; t < ROW_T; ++t) {
+                    state[t] = 0u;
+                    claim[t] = 0u;
+                    if ((uint32_t)(lane + 32 * t) < count && !bucket_match(bk[t], ent[t])) {
+                        const uint32_t em = bucket_match(bk[t], kInvalid);
+                        state[t] = em ? 1u : 2u;
+                        if (em) claim[t] = atomicCAS(s.vis.big + (size_t)hb[t] * 8 + (__ffs(em) - 1), kInvalid, ent[t]);
+                    }
+                }
                 bool ovf = false;
 #pragma unroll
                 for (int t = 0; t < ROW_T; ++t) {
-                    bool fresh = false;
-                    if ((uint32_t)(lane + 32 * t) < count) fresh = bucket_resolve(s.vis, ent[t], hb[t], bk[t], &ovf);
+                    bool fresh = state[t] == 1u && claim[t] == kInvalid;
+                    // lost the slot to another id of this row, or the bucket was full: general path on a fresh snapshot
+                    if (state[t] == 2u || (state[t] == 1u && claim[t] != kInvalid && claim[t] != ent[t]))
+                        fresh = bucket_resolve(s.vis, ent[t], hb[t], bucket_load(s.vis.big, hb[t]), &ovf);
                     const uint32_t m = __ballot_sync(kFullMask, fresh);
                     if (fresh) s.cpid[n_new + __popc(m & lt_mask)] = ent[t];
                     n_new += __popc(m);
