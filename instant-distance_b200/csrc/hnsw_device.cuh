@@ -31,7 +31,7 @@ constexpr int kSmallVisSlots = 512;           // shared-memory visited set used 
 constexpr int kTieCap = 1024;                 // per-warp tie list capacity (global memory)
 constexpr uint32_t kFullMask = 0xFFFFFFFFu;
 
-enum OptFlags : uint32_t { kOptPrefetchVectors = 1u, kOptPrefetchRows = 2u, kOptPrefetchNextRow = 8u };
+enum OptFlags : uint32_t { kOptPrefetchVectors = 1u, kOptPrefetchRows = 2u, kOptPrefetchNextRow = 8u, kOptFirstFreeSlot = 16u };
 
 enum QueryStatus : uint32_t { kQueryOk = 0, kQueryVisitedOverflow = 1, kQueryTieOverflow = 2 };
 
@@ -598,7 +598,11 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
                     if ((uint32_t)(lane + 32 * t) < count && !bucket_match(bk[t], ent[t])) {
                         const uint32_t em = bucket_match(bk[t], kInvalid);
                         state[t] = em ? 1u : 2u;
-                        if (em) claim[t] = atomicCAS(s.vis.big + (size_t)hb[t] * 8 + (__ffs(em) - 1), kInvalid, ent[t]);
+                        // lanes whose ids share a home bucket see the same free slots: spread their claims over them instead
+                        // of all taking the first one (a lost claim costs two more L2 round trips for the whole warp)
+                        uint32_t pick = __ffs(em) - 1;
+                        if (!(g.flags & kOptFirstFreeSlot)) pick = __fns(em, 0, ((((uint32_t)lane + 3u * t) & 7u) * __popc(em) >> 3) + 1);
+                        if (em) claim[t] = atomicCAS(s.vis.big + (size_t)hb[t] * 8 + pick, kInvalid, ent[t]);
                     }
                 }
                 bool ovf = false;
