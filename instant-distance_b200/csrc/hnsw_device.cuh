@@ -598,10 +598,12 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
                     if ((uint32_t)(lane + 32 * t) < count && !bucket_match(bk[t], ent[t])) {
                         const uint32_t em = bucket_match(bk[t], kInvalid);
                         state[t] = em ? 1u : 2u;
-                        // lanes whose ids share a home bucket see the same free slots: spread their claims over them instead
-                        // of all taking the first one (a lost claim costs two more L2 round trips for the whole warp)
+                        // ids that share a home bucket see the same free slots: spread their claims over them instead of all
+                        // taking the first one (a lost claim costs the whole warp two more L2 round trips).  The choice is a
+                        // function of the ID, not of the lane: the same id listed twice in a row must claim the same slot, so
+                        // that the atomicCAS lets it count once.
                         uint32_t pick = __ffs(em) - 1;
-                        if (!(g.flags & kOptFirstFreeSlot)) pick = __fns(em, 0, ((((uint32_t)lane + 3u * t) & 7u) * __popc(em) >> 3) + 1);
+                        if (!(g.flags & kOptFirstFreeSlot)) pick = __fns(em, 0, (((ent[t] * 0x85EBCA6Bu) >> 29) * __popc(em) >> 3) + 1);
                         if (em) claim[t] = atomicCAS(s.vis.big + (size_t)hb[t] * 8 + pick, kInvalid, ent[t]);
                     }
                 }
