@@ -361,7 +361,6 @@ idb_status Index::init_device(int dev) {
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (const char* e = std::getenv("IDB_OPT")) opt_flags = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("IDB_VIS_MULT")) vis_mult = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("IDB_L2_PERSIST")) l2_persist = std::atoi(e) != 0;
     if (const char* e = std::getenv("IDB_CTAS_PER_SM")) ctas_per_sm = std::min(kMaxCtasPerSm, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("IDB_VARIANT")) variant = std::atoi(e);
     if (const char* e = std::getenv("IDB_VIS_BITMAP")) vis_bitmap = std::atoi(e);

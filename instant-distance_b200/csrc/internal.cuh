@@ -99,10 +99,9 @@ struct Index {
 
     Scratch sc;
     uint64_t last_nq = 0;
-    // tuning knobs (env IDB_OPT / IDB_VIS_MULT / IDB_L2_PERSIST / IDB_CTAS_PER_SM); none of them changes results
+    // tuning knobs (env IDB_OPT / IDB_VIS_MULT / IDB_VIS_BUCKETS / IDB_VIS_BITMAP / IDB_CTAS_PER_SM); none of them changes results
     uint32_t opt_flags = 0;       // L2 prefetch of rows/vectors: measured neutral-to-negative once 16 rows are in flight (profiles/r01_call4)
     uint32_t vis_mult = 4;        // visited table slots = next_pow2(vis_mult * 2M * ef): load <= ~0.15, probe chains ~1
-    bool l2_persist = false;      // pin the visited tables in L2 with an access-policy window
     int ctas_per_sm = kSearchCtasPerSm;
     uint32_t vis_slots_override = 0; // IDB_VIS_SLOTS (tests): exact per-warp visited-table size, to force the overflow -> retry path
     int vis_bitmap = 1;           // IDB_VIS_BITMAP: 0 hash set, 1 bitmap over PointIds when it is no bigger than 2x the hash table
