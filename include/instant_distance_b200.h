@@ -100,7 +100,11 @@ IDB_API idb_status idb_index_from_graph_bf16(const float* points, uint64_t n, ui
  * The reference returns the whole `nearest` list (<= ef_search items, ascending by (distance, pid));
  * callers take the first k.  Here: out_ids/out_dist are nq x k (row q holds the first min(len,k) items,
  * padded with IDB_INVALID / +inf), out_len[q] = len(nearest) (what `ExactSizeIterator::len` reports).
- * ef_search == 0 uses the index's own ef_search (Hnsw::ef_search, core:195).  out_dist / out_len may be NULL. */
+ * ef_search == 0 uses the index's own ef_search (Hnsw::ef_search, core:195).  out_dist / out_len may be NULL.
+ * Device-wide side effect: when the per-warp visited tables of the search kernel fit it (e.g. M = 32, ef_search <= 100), the first
+ * search of an index reserves the device's persisting-L2 set-aside (cudaLimitPersistingL2CacheSize, up to the device maximum) and
+ * attaches an access-policy window for those tables to the index's stream; both are returned when the last such index is freed.
+ * IDB_VIS_BUCKETS=0 in the environment opts out (the tables then live in HBM; results are identical, throughput ~10 % lower). */
 IDB_API idb_status idb_search_batch_f32(idb_index* index, const float* queries, uint64_t nq, uint32_t ef_search, uint32_t k,
                                 uint32_t* out_ids, float* out_dist, uint32_t* out_len);
 
