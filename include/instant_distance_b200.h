@@ -101,19 +101,37 @@ IDB_API idb_status idb_index_from_graph_bf16(const float* points, uint64_t n, ui
  * callers take the first k.  Here: out_ids/out_dist are nq x k (row q holds the first min(len,k) items,
  * padded with IDB_INVALID / +inf), out_len[q] = len(nearest) (what `ExactSizeIterator::len` reports).
  * ef_search == 0 uses the index's own ef_search (Hnsw::ef_search, core:195).  out_dist / out_len may be NULL.
- * Device-wide side effect: when the per-warp visited tables of the search kernel fit it (e.g. M = 32, ef_search <= 100), the first
- * search of an index reserves the device's persisting-L2 set-aside (cudaLimitPersistingL2CacheSize, up to the device maximum) and
- * attaches an access-policy window for those tables to the index's stream; both are returned when the last such index is freed.
- * IDB_VIS_BUCKETS=0 in the environment opts out (the tables then live in HBM; results are identical, throughput ~10 % lower). */
+ * Thread safety: `Hnsw<P>: Sync` (core:352-356) — any number of host threads may call this on one index at once; each call
+ * takes an idle submission lane (own CUDA stream and control state, idb_index_num_lanes() of them) so concurrent callers overlap on
+ * the device.
+ * Device-wide side effect: the per-warp visited tables of the traversal kernels live in a per-device pool shared by every index; the
+ * first search/build on a device reserves part of the device's persisting-L2 set-aside for them (cudaLimitPersistingL2CacheSize, as
+ * much as the tables in use need, at most the device maximum) and every launch carries an access-policy window for them as a launch
+ * attribute (no stream state).  The reservation is returned when the last index on the device is freed.  A host application that
+ * manages the persisting L2 itself calls idb_device_set_persisting_l2(device, 0) (or sets IDB_L2_PERSIST=0): results are identical,
+ * throughput ~10 % lower. */
 IDB_API idb_status idb_search_batch_f32(idb_index* index, const float* queries, uint64_t nq, uint32_t ef_search, uint32_t k,
                                 uint32_t* out_ids, float* out_dist, uint32_t* out_len);
 
 /* Same, with queries and outputs already resident in HBM (device pointers, same device as the index;
- * d_queries is nq x dim row-major).  Enqueues on idb_index_stream(index) and returns without syncing. */
+ * d_queries is nq x dim row-major).  Enqueues on idb_index_stream(index) (= lane 0) and returns without syncing.
+ * A query that overflows an internal per-query structure even in the retry pass gets out_len = 0 and IDB_INVALID ids;
+ * idb_last_search_failures() reports how many did (the host-buffer call returns IDB_ERR_CAPACITY instead). */
 IDB_API idb_status idb_search_batch_device(idb_index* index, const float* d_queries, uint64_t nq, uint32_t ef_search, uint32_t k,
                                    uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len);
+/* The same on submission lane `lane` < idb_index_num_lanes(): calls on one lane are stream-ordered (idb_index_lane_stream), calls
+ * on different lanes overlap — the next batch's thread blocks move in as the previous batch's drain, so back-to-back batches
+ * issued alternately on two lanes keep the GPU full across batch boundaries. */
+IDB_API idb_status idb_search_batch_device_lane(idb_index* index, uint32_t lane, const float* d_queries, uint64_t nq, uint32_t ef_search,
+                                        uint32_t k, uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len);
+IDB_API uint32_t idb_index_num_lanes(void);
+IDB_API void* idb_index_lane_stream(idb_index* index, uint32_t lane);  /* cudaStream_t of that lane */
+/* Waits for the last call on `lane` and reports how many of its queries failed even in the retry pass (0 = all results valid). */
+IDB_API idb_status idb_last_search_failures(idb_index* index, uint32_t lane, uint32_t* out_failed);
+/* enabled = 0: this library never touches the device's persisting-L2 limit nor attaches access-policy windows on `device`. */
+IDB_API idb_status idb_device_set_persisting_l2(int32_t device, int32_t enabled);
 
-/* Per-query traversal counters of the LAST search call on this index (for the roofline accounting,
+/* Per-query traversal counters of the LAST search call issued on this index (whichever lane it used; for the roofline accounting,
  * SURVEY §8d): out is nq x 4 u64 = {n_expand_upper, n_dist_upper, n_expand_zero, n_dist_zero}. */
 IDB_API idb_status idb_last_search_counters(idb_index* index, uint64_t nq, uint64_t* out);
 
@@ -156,8 +174,8 @@ IDB_API idb_status idb_debug_gather_bench(idb_index* index, uint32_t n_items, ui
 IDB_API idb_status idb_debug_gather_mix_bench(idb_index* index, uint32_t n_items, uint32_t batches, uint32_t chain, uint32_t reps,
                                               uint32_t atomics_per_batch, uint32_t mode, float* out_ms, double* out_bytes);
 
-IDB_API void* idb_index_stream(idb_index* index);      /* the cudaStream_t all work of this index is enqueued on */
-IDB_API idb_status idb_index_sync(idb_index* index);   /* cudaStreamSynchronize on it */
+IDB_API void* idb_index_stream(idb_index* index);      /* lane 0's cudaStream_t: builds, uploads and idb_search_batch_device run on it */
+IDB_API idb_status idb_index_sync(idb_index* index);   /* cudaStreamSynchronize on every lane of the index */
 IDB_API void idb_index_free(idb_index* index);         /* Drop for Hnsw */
 
 /* ---- Index sharded by PointId range across the GPUs of one box (one process per GPU) ------------------------------

@@ -27,21 +27,21 @@ idb_status fail(idb_status st, const char* fmt, ...) {
 }
 
 // one translation unit per CH (search_chN.cu)
-cudaError_t dispatch_search_ch1(const SearchArgs&, int, int, int, cudaStream_t);
-cudaError_t dispatch_search_ch2(const SearchArgs&, int, int, int, cudaStream_t);
-cudaError_t dispatch_search_ch3(const SearchArgs&, int, int, int, cudaStream_t);
-cudaError_t dispatch_search_ch4(const SearchArgs&, int, int, int, cudaStream_t);
-cudaError_t dispatch_search_ch6(const SearchArgs&, int, int, int, cudaStream_t);
-cudaError_t dispatch_search_ch8(const SearchArgs&, int, int, int, cudaStream_t);
+cudaError_t dispatch_search_ch1(const SearchArgs&, int, int, int, cudaStream_t, const LaunchWindow&);
+cudaError_t dispatch_search_ch2(const SearchArgs&, int, int, int, cudaStream_t, const LaunchWindow&);
+cudaError_t dispatch_search_ch3(const SearchArgs&, int, int, int, cudaStream_t, const LaunchWindow&);
+cudaError_t dispatch_search_ch4(const SearchArgs&, int, int, int, cudaStream_t, const LaunchWindow&);
+cudaError_t dispatch_search_ch6(const SearchArgs&, int, int, int, cudaStream_t, const LaunchWindow&);
+cudaError_t dispatch_search_ch8(const SearchArgs&, int, int, int, cudaStream_t, const LaunchWindow&);
 
-cudaError_t dispatch_search(const SearchArgs& a, int ch, int row_t, int ef_t, int grid, cudaStream_t st) {
+cudaError_t dispatch_search(const SearchArgs& a, int ch, int row_t, int ef_t, int grid, cudaStream_t st, const LaunchWindow& win) {
     switch (ch) {
-        case 1: return dispatch_search_ch1(a, row_t, ef_t, grid, st);
-        case 2: return dispatch_search_ch2(a, row_t, ef_t, grid, st);
-        case 3: return dispatch_search_ch3(a, row_t, ef_t, grid, st);
-        case 4: return dispatch_search_ch4(a, row_t, ef_t, grid, st);
-        case 5: case 6: return dispatch_search_ch6(a, row_t, ef_t, grid, st);
-        default: return dispatch_search_ch8(a, row_t, ef_t, grid, st);
+        case 1: return dispatch_search_ch1(a, row_t, ef_t, grid, st, win);
+        case 2: return dispatch_search_ch2(a, row_t, ef_t, grid, st, win);
+        case 3: return dispatch_search_ch3(a, row_t, ef_t, grid, st, win);
+        case 4: return dispatch_search_ch4(a, row_t, ef_t, grid, st, win);
+        case 5: case 6: return dispatch_search_ch6(a, row_t, ef_t, grid, st, win);
+        default: return dispatch_search_ch8(a, row_t, ef_t, grid, st, win);
     }
 }
 
@@ -84,6 +84,32 @@ __global__ void validate_rows_kernel(const uint32_t* rows, size_t count, uint32_
     }
 }
 
+// Does any adjacency row list a PointId twice?  (The b16 visited flavour assumes it does not; graphs built by this library or by the
+// reference never do.)  One warp per row of `width` <= 128 entries.
+__global__ void repeated_ids_kernel(const uint32_t* rows, size_t n_rows, uint32_t width, uint32_t* repeats) {
+    const int lane = threadIdx.x & 31;
+    const size_t wpb = blockDim.x >> 5;
+    for (size_t r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rows; r += (size_t)gridDim.x * wpb) {
+        uint32_t e[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) e[t] = (uint32_t)(lane + 32 * t) < width ? rows[r * width + lane + 32 * t] : kInvalid;
+        bool rep = false;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint32_t peers = __match_any_sync(kFullMask, e[t] == kInvalid ? (0x80000000u | (uint32_t)lane) + 0u : e[t]);
+            rep |= e[t] != kInvalid && (peers & ((1u << lane) - 1u));
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2)
+                if (t2 > t)
+                    for (int src = 0; src < 32; ++src) {
+                        const uint32_t o = __shfl_sync(kFullMask, e[t], src);
+                        rep |= o != kInvalid && o == e[t2];
+                    }
+        }
+        if (__any_sync(kFullMask, rep) && lane == 0) atomicAdd(repeats, 1u);
+    }
+}
+
 __global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -120,148 +146,272 @@ cudaError_t ensure_u64(uint64_t*& p, size_t& cap, size_t need) { return ensure(p
 cudaError_t ensure_f32(float*& p, size_t& cap, size_t need) { return ensure(p, cap, need); }
 
 
-static std::atomic<int> g_persist_users{0};  // live indexes holding bucket tables (they share the device's persisting-L2 set-aside)
+// ---------------------------------------------------------------------------------------------------------
+// DeviceCtx: the per-device pool of per-warp scratch tables
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_ctx_mu;
+DeviceCtx* g_ctx[64] = {};
+int g_l2_pref[64] = {};  // idb_device_set_persisting_l2: 0 default (allowed), -1 disabled
+}  // namespace
 
-idb_status Index::ensure_search_scratch(uint32_t ef, uint64_t nq, uint32_t k) {
-    // visited tables: one per resident warp, sized for >= 2x the worst plausible number of visited ids (2M per expansion)
-    uint32_t want_slots = std::max<uint32_t>(1024u, next_pow2((uint64_t)vis_mult * 2 * M * std::max<uint32_t>(ef, 16u)));
-    if (vis_slots_override) want_slots = vis_slots_override;  // tests: force the overflow -> retry path
-    const uint32_t warps = (uint32_t)search_grid() * kSearchWarps;
-    // bitmap flavour of the big tier: n bits per warp, used when that is no bigger than twice the hash table
-    const uint32_t bm_words = (uint32_t)std::min<uint64_t>(((n + 31) / 32 + 127) / 128 * 128, 0xFFFFFF80u);
-    sc.bm_words = (vis_bitmap && !vis_slots_override && (n + 31) / 32 <= 2ull * want_slots) ? bm_words : 0u;
-    const uint32_t want_stride = std::max(want_slots, sc.bm_words);
-    if (want_slots > sc.gslots || want_stride > sc.vis_stride || !sc.vis_tables || (vis_slots_override && want_slots != sc.gslots)) {
-        if (sc.vis_tables) cudaFree(sc.vis_tables);
-        sc.vis_tables = nullptr;
-        size_t words = (size_t)warps * want_stride;
-        CUDA_TRY(cudaMalloc(&sc.vis_tables, words * 4));
-        CUDA_TRY(fill_u32(sc.vis_tables, words, kInvalid, stream));
-        sc.vis_stride = want_stride;
-        sc.gslots = want_slots;
+TablePool DeviceCtx::main_pool(bool b16) const {
+    TablePool tp;
+    tp.slot_masks = slot_masks;
+    tp.fixed_word = -1;
+    tp.word_base = 0;
+    tp.slots_per_word = (uint32_t)slots_per_sm;
+    tp.vis_tables = b16 ? b16_tables : big_tables;
+    tp.vis_stride = b16 ? b16_stride : big_stride;
+    tp.tie_tables = tie_tables;
+    tp.tie_cap = kTieCap;
+    return tp;
+}
+TablePool DeviceCtx::retry_pool() const {
+    TablePool tp;
+    tp.slot_masks = slot_masks;
+    tp.fixed_word = num_sms;
+    tp.word_base = (uint32_t)num_sms;
+    tp.slots_per_word = kRetryCtas;
+    tp.vis_tables = retry_tables;
+    tp.vis_stride = kRetrySlots;
+    tp.tie_tables = retry_ties;
+    tp.tie_cap = kRetryTieCap;
+    return tp;
+}
+
+idb_status DeviceCtx::acquire(int device, DeviceCtx** out) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (device < 0 || device >= 64) return fail(IDB_ERR_INVALID_ARG, "device %d out of range", device);
+    if (g_ctx[device]) {
+        g_ctx[device]->refs++;
+        *out = g_ctx[device];
+        return IDB_OK;
     }
-    // bucket-set flavour (K1's default when it fits): ~1.25 slots per id a query can possibly visit (2M per expansion, ~ef
-    // expansions), compact tables, kept in the persisting part of L2 by an access-policy window on this index's stream.
-    sc.bucket_slots = 0;
-    if (vis_buckets && !vis_slots_override) {
-        uint32_t slots = std::max<uint32_t>(1024u, next_pow2(((uint64_t)5 * 2 * M * std::max<uint32_t>(ef, 16u) + 3) / 4));
-        if (bucket_slots_override) slots = bucket_slots_override;  // tests: force the overflow -> retry path
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
-        const size_t bytes = (size_t)warps * slots * 4;
-        if (vis_buckets > 1 || (bytes <= (size_t)max_persist && bytes <= (size_t)max_window)) {
-            if (slots != sc.bucket_cap || !sc.bucket_tables) {
-                if (!sc.bucket_tables) g_persist_users.fetch_add(1);
-                if (sc.bucket_tables) cudaFree(sc.bucket_tables);
-                sc.bucket_tables = nullptr;
-                CUDA_TRY(cudaMalloc(&sc.bucket_tables, bytes));
-                CUDA_TRY(fill_u32(sc.bucket_tables, (size_t)warps * slots, kInvalid, stream));
-                sc.bucket_cap = slots;
-                if (max_persist > 0 && max_window > 0) {
-                    const size_t carve = std::min<size_t>(bytes, (size_t)max_persist);
-                    CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
-                    cudaStreamAttrValue av;
-                    std::memset(&av, 0, sizeof(av));
-                    av.accessPolicyWindow.base_ptr = sc.bucket_tables;
-                    av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)max_window);
-                    av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)av.accessPolicyWindow.num_bytes);
-                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                    CUDA_TRY(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
-                }
-            }
-            sc.bucket_slots = slots;
-        }
-    }
-    if (!sc.retry_tables) {
-        size_t words = (size_t)kRetryWarps * kRetrySlots;
-        CUDA_TRY(cudaMalloc(&sc.retry_tables, words * 4));
-        CUDA_TRY(fill_u32(sc.retry_tables, words, kInvalid, stream));
-    }
-    if (!sc.tie_tables) CUDA_TRY(cudaMalloc(&sc.tie_tables, (size_t)(warps + kRetryWarps) * kTieCap * 8));
-    if (!sc.ctrl) CUDA_TRY(cudaMalloc(&sc.ctrl, 64));
-    CUDA_TRY(ensure(sc.status, sc.status_cap, nq));
-    CUDA_TRY(ensure(sc.fail_list, sc.fail_cap, nq));
-    CUDA_TRY(ensure(sc.counters, sc.counters_cap, nq * 4));
-    (void)k;
+    auto* c = new (std::nothrow) DeviceCtx();
+    if (!c) return fail(IDB_ERR_OOM, "host allocation failed");
+    c->device = device;
+    cudaDeviceProp prop;
+    auto bail = [&](cudaError_t e, int line) {
+        delete c;
+        return fail(e == cudaErrorMemoryAllocation ? IDB_ERR_OOM : IDB_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e), __FILE__,
+                    line, cudaGetErrorString(e));
+    };
+#define CTX_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return bail(e_, __LINE__); } while (0)
+    CTX_TRY(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    if (const char* e = std::getenv("IDB_CTAS_PER_SM")) c->slots_per_sm = std::min(kMaxCtasPerSm, std::max(1, std::atoi(e)));
+    c->n_tables = (uint32_t)c->num_sms * (uint32_t)c->slots_per_sm * kSearchWarps;
+    cudaDeviceGetAttribute(&c->max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+    cudaDeviceGetAttribute(&c->max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+    c->l2_allowed = g_l2_pref[device] >= 0;
+    if (const char* e = std::getenv("IDB_L2_PERSIST")) c->l2_allowed = c->l2_allowed && std::atoi(e) != 0;
+    // b16 tables: as many bytes per warp as keep ALL tables inside the persisting part of L2 (34 KB on B200: 79 MB / 2368 warps)
+    size_t per = c->max_persist > 0 ? (size_t)c->max_persist / c->n_tables : (size_t)32 * 1024;
+    per = std::min<size_t>(std::max<size_t>(per / 512 * 512, 8 * 1024), 64 * 1024);
+    c->b16_stride = (uint32_t)(per / 4);
+    CTX_TRY(cudaMalloc(&c->slot_masks, ((size_t)c->num_sms + 1) * 4));
+    CTX_TRY(cudaMemset(c->slot_masks, 0, ((size_t)c->num_sms + 1) * 4));
+    CTX_TRY(cudaMalloc(&c->b16_tables, (size_t)c->n_tables * per));
+    CTX_TRY(cudaMemset(c->b16_tables, 0xFF, (size_t)c->n_tables * per));
+    const size_t retry_words = (size_t)kRetryCtas * kSearchWarps * kRetrySlots;
+    CTX_TRY(cudaMalloc(&c->retry_tables, retry_words * 4));
+    CTX_TRY(cudaMemset(c->retry_tables, 0xFF, retry_words * 4));
+    CTX_TRY(cudaMalloc(&c->tie_tables, (size_t)c->n_tables * kTieCap * 8));
+    CTX_TRY(cudaMalloc(&c->retry_ties, (size_t)kRetryCtas * kSearchWarps * kRetryTieCap * 8));
+    CTX_TRY(cudaDeviceSynchronize());
+#undef CTX_TRY
+    c->refs = 1;
+    g_ctx[device] = c;
+    *out = c;
     return IDB_OK;
 }
 
-int Index::search_grid() const { return num_sms * ctas_per_sm; }
+void DeviceCtx::release(DeviceCtx* c) {
+    if (!c) return;
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (--c->refs > 0) return;
+    g_ctx[c->device] = nullptr;
+    delete c;
+}
 
-// Enqueue one batched search; all pointers are device pointers, d_queries padded to nchunks*4 floats per row.
-idb_status Index::enqueue_search(const float* d_queries_padded, uint64_t nq, uint32_t ef, uint32_t k, uint32_t* d_ids,
-                                 float* d_dist, uint32_t* d_len) {
-    if (ef > 512) return fail(IDB_ERR_UNSUPPORTED, "ef_search %u > 512 is not supported yet", ef);
-    idb_status st = ensure_search_scratch(ef, nq, k);
+DeviceCtx::~DeviceCtx() {
+    cudaSetDevice(device);
+    cudaDeviceSynchronize();
+    if (l2_reserved) {  // hand the persisting lines and the device's L2 set-aside back
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    }
+    cudaFree(slot_masks);
+    cudaFree(b16_tables);
+    cudaFree(big_tables);
+    cudaFree(retry_tables);
+    cudaFree(tie_tables);
+    cudaFree(retry_ties);
+}
+
+idb_status DeviceCtx::ensure_big(uint32_t stride_words) {
+    if (big_tables && stride_words <= big_stride) return IDB_OK;
+    CUDA_TRY(cudaDeviceSynchronize());  // nobody may be using the old tables (enqueues are serialised by mu)
+    cudaFree(big_tables);
+    big_tables = nullptr;
+    big_stride = 0;
+    const size_t words = (size_t)n_tables * stride_words;
+    CUDA_TRY(cudaMalloc(&big_tables, words * 4));
+    CUDA_TRY(cudaMemset(big_tables, 0xFF, words * 4));
+    CUDA_TRY(cudaDeviceSynchronize());
+    big_stride = stride_words;
+    return IDB_OK;
+}
+
+idb_status DeviceCtx::reserve_l2(size_t bytes) {
+    if (!l2_allowed || max_persist <= 0 || max_window <= 0) return IDB_OK;
+    bytes = std::min<size_t>(bytes, (size_t)max_persist);
+    if (bytes <= l2_reserved) return IDB_OK;
+    CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
+    l2_reserved = bytes;
+    return IDB_OK;
+}
+
+void Lane::free_all() {
+    cudaFree(ctrl); cudaFree(status); cudaFree(fail_list); cudaFree(counters);
+    cudaFree(q); cudaFree(ids); cudaFree(dist); cudaFree(len);
+    cudaFree(keys_local); cudaFree(keys_all); cudaFree(q2); cudaFree(ids2);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+Lane& Index::pick_lane() {
+    // prefer an idle lane; otherwise queue behind the next one in rotation
+    for (int i = 0; i < kLanes; ++i) {
+        Lane& ln = lanes[(next_lane.load() + i) % kLanes];
+        if (ln.mu.try_lock()) {
+            next_lane.fetch_add(i + 1);
+            return ln;
+        }
+    }
+    Lane& ln = lanes[next_lane.fetch_add(1) % kLanes];
+    ln.mu.lock();
+    return ln;
+}
+
+idb_status Index::ensure_lane_scratch(Lane& ln, uint64_t nq) {
+    if (!ln.ctrl) CUDA_TRY(cudaMalloc(&ln.ctrl, 64));
+    CUDA_TRY(ensure(ln.status, ln.status_cap, nq));
+    CUDA_TRY(ensure(ln.fail_list, ln.fail_cap, nq));
+    CUDA_TRY(ensure(ln.counters, ln.counters_cap, nq * 4));
+    if (profiling && !ln.ev0) {
+        CUDA_TRY(cudaEventCreate(&ln.ev0));
+        CUDA_TRY(cudaEventCreate(&ln.ev1));
+    }
+    return IDB_OK;
+}
+
+// Which flavour of the big visited tier serves a traversal with this ef, and where its tables are.
+//   b16 (default): exact while ceil(n / 32768) <= buckets and no adjacency row repeats an id; ~2 u16 slots per id the traversal can
+//     possibly visit (2M per expansion, ~ef expansions), clamped to the per-warp stride (= what fits the persisting part of L2);
+//   else bitmap (n bits per warp) when that is no bigger than 2x the hash table, else the hash set.
+idb_status Index::select_visited_tier(uint32_t ef, SearchArgs& a, LaunchWindow& win) {
+    DeviceCtx& c = *ctx;
+    const uint32_t efx = std::max<uint32_t>(ef, 16u);
+    uint32_t b16_bytes = (uint32_t)std::min<uint64_t>(((uint64_t)2 * M * efx * 4 + 511) / 512 * 512, (uint64_t)c.b16_stride * 4);
+    if (b16_bytes_override) b16_bytes = std::min<uint32_t>(std::max<uint32_t>(b16_bytes_override / 32 * 32, 64u), c.b16_stride * 4);
+    const uint32_t nb = b16_bytes / 32;
+    const bool b16_exact = rows_distinct && (n + 32767) / 32768 <= nb;
+    int tier = vis_tier;
+    if (tier < 0 || (tier == 2 && !b16_exact)) tier = b16_exact ? 2 : -1;
+    win = LaunchWindow();
+    if (tier == 2) {
+        a.pool = c.main_pool(true);
+        a.gslots = nb * 8;
+        a.gshift = 0;
+        a.vis_mode = kVisB16;
+        a.b16_cap_ids = nb * 11;  // <= 11 of 16 slots on average; fuller tables hand the query to the retry pass
+        idb_status st = c.reserve_l2((size_t)c.n_tables * b16_bytes);
+        if (st != IDB_OK) return st;
+        if (c.l2_reserved) {
+            win.base = c.b16_tables;
+            win.bytes = std::min<size_t>((size_t)c.n_tables * c.b16_stride * 4, (size_t)c.max_window);
+            win.hit_ratio = 1.0f;  // only the first b16_bytes of every stride are ever touched
+        }
+        return IDB_OK;
+    }
+    uint32_t want_slots = std::max<uint32_t>(1024u, next_pow2((uint64_t)vis_mult * 2 * M * efx));
+    if (vis_slots_override) want_slots = vis_slots_override;  // tests: force the overflow -> retry path
+    const uint32_t bm_words = (uint32_t)std::min<uint64_t>(((n + 31) / 32 + 127) / 128 * 128, 0xFFFFFF80u);
+    const bool bitmap = tier == 1 || (tier < 0 && !vis_slots_override && (n + 31) / 32 <= 2ull * want_slots);
+    idb_status st = c.ensure_big(std::max(want_slots, bitmap ? bm_words : 0u));
     if (st != IDB_OK) return st;
-    CUDA_TRY(cudaMemsetAsync(sc.ctrl, 0, 64, stream));
+    a.pool = c.main_pool(false);
+    a.gslots = bitmap ? bm_words : want_slots;
+    a.gshift = 32 - (uint32_t)std::log2((double)want_slots);
+    a.vis_mode = bitmap ? kVisBitmap : kVisHash;
+    a.b16_cap_ids = 0;
+    return IDB_OK;
+}
+
+int Index::search_grid() const { return num_sms * ctx->slots_per_sm; }
+
+// Enqueue one batched search on a lane; all pointers are device pointers, d_queries padded to nchunks*4 floats per row.
+// The caller holds ln.mu.
+idb_status Index::enqueue_search(Lane& ln, const float* d_queries_padded, uint64_t nq, uint32_t ef, uint32_t k, uint32_t* d_ids,
+                                 float* d_dist, uint32_t* d_len, uint64_t* out_keys) {
+    if (n) ef = (uint32_t)std::min<uint64_t>(ef, n);  // admission is rank < ef and there are only n distinct ids: same results
+    if (ef > 1024) return fail(IDB_ERR_UNSUPPORTED, "ef_search %u > 1024 (on an index of more than 1024 points) is not supported", ef);
+    idb_status st = ensure_lane_scratch(ln, nq);
+    if (st != IDB_OK) return st;
+    CUDA_TRY(cudaMemsetAsync(ln.ctrl, 0, 64, ln.stream));
 
     SearchArgs a;
+    std::memset(&a, 0, sizeof(a));
     a.g = view();
     a.queries = reinterpret_cast<const float4*>(d_queries_padded);
     a.n_work = nq;
-    a.n_work_dev = nullptr;
-    a.work_list = nullptr;
     a.ef = ef;
     a.k = k;
     a.out_ids = d_ids;
     a.out_dist = d_dist;
     a.out_len = d_len;
-    a.counters = sc.counters;
-    a.status = sc.status;
-    a.work_counter = reinterpret_cast<unsigned long long*>(sc.ctrl);
-    a.fail_count = reinterpret_cast<uint32_t*>(sc.ctrl + 16);
-    a.fail_list = sc.fail_list;
-    if (sc.bucket_slots) {
-        a.vis_tables = sc.bucket_tables;
-        a.gslots = sc.bucket_slots;
-        a.gshift = 32 - (uint32_t)std::log2((double)sc.bucket_slots);
-        a.vis_stride = sc.bucket_slots;
-        a.vis_mode = kVisBuckets;
-    } else {
-        a.vis_tables = sc.vis_tables;
-        a.gslots = sc.bm_words ? sc.bm_words : sc.gslots;
-        a.gshift = 32 - (uint32_t)std::log2((double)sc.gslots);
-        a.vis_stride = sc.vis_stride;
-        a.vis_mode = sc.bm_words ? kVisBitmap : kVisHash;
-    }
-    a.tie_tables = sc.tie_tables;
+    a.counters = ln.counters;
+    a.status = ln.status;
+    a.work_counter = reinterpret_cast<unsigned long long*>(ln.ctrl);
+    a.fail_count = reinterpret_cast<uint32_t*>(ln.ctrl + 16);
+    a.fail_list = ln.fail_list;
     a.variant = variant;
-    a.out_keys = pending_out_keys;
+    a.out_keys = out_keys;
     a.id_map = d_id_map;
 
     const int ch = (int)((nchunks + 31) / 32);
     if (ch > 8) return fail(IDB_ERR_UNSUPPORTED, "dim %u > 1024 is not supported yet", dim);
     const int row_t = (int)((2 * M + 31) / 32);
     const int ef_t = (int)((ef + 31) / 32);
-    const uint64_t warps_needed = nq;
-    int grid = search_grid();
-    const int min_grid = (int)std::min<uint64_t>((warps_needed + kSearchWarps - 1) / kSearchWarps, (uint64_t)grid);
-    grid = std::max(1, min_grid);
-    if (profiling) CUDA_TRY(cudaEventRecord(ev0, stream));
-    CUDA_TRY(dispatch_search(a, ch, row_t, ef_t, grid, stream));
-    if (profiling) CUDA_TRY(cudaEventRecord(ev1, stream));
-    last_launches = 2;  // K1 + the (normally idle) retry pass
+    const int grid = std::max(1, (int)std::min<uint64_t>((nq + kSearchWarps - 1) / kSearchWarps, (uint64_t)search_grid()));
+
+    std::lock_guard<std::mutex> lk(ctx->mu);  // the tables this launch uses must not be regrown under it
+    LaunchWindow win;
+    st = select_visited_tier(ef, a, win);
+    if (st != IDB_OK) return st;
+    if (profiling) CUDA_TRY(cudaEventRecord(ln.ev0, ln.stream));
+    CUDA_TRY(dispatch_search(a, ch, row_t, ef_t, grid, ln.stream, win));
+    if (profiling) CUDA_TRY(cudaEventRecord(ln.ev1, ln.stream));
+    ln.last_launches = 2;  // K1 + the (normally idle) retry pass
 
     // Retry pass (device-side, unconditional, normally a no-op): queries whose visited table overflowed are re-run
-    // by a few warps with 2^21-slot tables.  n_work is read from fail_count on the device.
+    // by a few warps with 2^21-slot hash sets.  n_work is read from fail_count on the device.
     SearchArgs r = a;
-    r.work_list = sc.fail_list;
+    r.work_list = ln.fail_list;
     r.n_work_dev = a.fail_count;
     r.n_work = 0;
-    r.work_counter = reinterpret_cast<unsigned long long*>(sc.ctrl + 32);
-    r.fail_count = reinterpret_cast<uint32_t*>(sc.ctrl + 48);
+    r.work_counter = reinterpret_cast<unsigned long long*>(ln.ctrl + 32);
+    r.fail_count = reinterpret_cast<uint32_t*>(ln.ctrl + 48);
     r.fail_list = nullptr;       // failures of the retry pass are only counted (and visible in status[])
-    r.vis_tables = sc.retry_tables;
+    r.pool = ctx->retry_pool();
     r.gslots = kRetrySlots;
     r.gshift = 32 - 21;
-    r.vis_stride = kRetrySlots;
     r.vis_mode = kVisHash;
-    r.tie_tables = sc.tie_tables + (size_t)search_grid() * kSearchWarps * kTieCap;
-    CUDA_TRY(dispatch_search(r, ch, row_t, ef_t, kRetryWarps / kSearchWarps, stream));
-    last_nq = nq;
+    CUDA_TRY(dispatch_search(r, ch, row_t, ef_t, kRetryCtas, ln.stream, LaunchWindow()));
+    ln.last_nq = nq;
     return IDB_OK;
 }
 
@@ -312,36 +462,16 @@ GraphView Index::view() const {
 
 Index::~Index() {
     cudaSetDevice(device);
-    if (stream) cudaStreamSynchronize(stream);
+    for (auto& ln : lanes)
+        if (ln.stream) cudaStreamSynchronize(ln.stream);
     cudaFree(d_points);
     cudaFree(d_points_bf16);
     cudaFree(d_zero);
     for (auto* p : d_upper) cudaFree(p);
     cudaFree(d_upper_ptrs);
-    cudaFree(sc.vis_tables);
-    if (sc.bucket_tables) {  // hand the persisting lines back; the last user also returns the L2 set-aside
-        cudaCtxResetPersistingL2Cache();
-        if (g_persist_users.fetch_sub(1) == 1) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
-    }
-    cudaFree(sc.bucket_tables);
-    cudaFree(sc.retry_tables);
-    cudaFree(sc.tie_tables);
-    cudaFree(sc.ctrl);
-    cudaFree(sc.status);
-    cudaFree(sc.fail_list);
-    cudaFree(sc.counters);
-    cudaFree(sc.q);
-    cudaFree(sc.ids);
-    cudaFree(sc.dist);
-    cudaFree(sc.len);
-    cudaFree(sc.keys_local);
-    cudaFree(sc.keys_all);
-    cudaFree(sc.q2);
-    cudaFree(sc.ids2);
     cudaFree(d_id_map);
-    if (ev0) cudaEventDestroy(ev0);
-    if (ev1) cudaEventDestroy(ev1);
-    if (stream) cudaStreamDestroy(stream);
+    for (auto& ln : lanes) ln.free_all();
+    DeviceCtx::release(ctx);
 }
 
 idb_status Index::init_device(int dev) {
@@ -358,14 +488,15 @@ idb_status Index::init_device(int dev) {
     if (prop.major < 10)
         return fail(IDB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
     num_sms = prop.multiProcessorCount;
-    CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    idb_status st = DeviceCtx::acquire(dev, &ctx);
+    if (st != IDB_OK) return st;
+    for (auto& ln : lanes) CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+    stream = lanes[0].stream;
     if (const char* e = std::getenv("IDB_OPT")) opt_flags = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("IDB_VIS_MULT")) vis_mult = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("IDB_CTAS_PER_SM")) ctas_per_sm = std::min(kMaxCtasPerSm, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("IDB_VARIANT")) variant = std::atoi(e);
-    if (const char* e = std::getenv("IDB_VIS_BITMAP")) vis_bitmap = std::atoi(e);
-    if (const char* e = std::getenv("IDB_VIS_BUCKETS")) vis_buckets = std::atoi(e);
-    if (const char* e = std::getenv("IDB_BUCKET_SLOTS")) bucket_slots_override = next_pow2((uint64_t)std::max(64, std::atoi(e)));
+    if (const char* e = std::getenv("IDB_VIS_TIER")) vis_tier = std::atoi(e);
+    if (const char* e = std::getenv("IDB_B16_BYTES")) b16_bytes_override = (uint32_t)std::max(64, std::atoi(e));
     if (const char* e = std::getenv("IDB_VIS_SLOTS")) vis_slots_override = next_pow2((uint64_t)std::max(64, std::atoi(e)));
     return IDB_OK;
 }
@@ -373,6 +504,14 @@ idb_status Index::init_device(int dev) {
 // Upload a graph (host arrays) into HBM.
 idb_status Index::upload(const float* points, uint64_t n_, uint32_t dim_, uint32_t M_, uint32_t ef, const uint32_t* zero,
                          uint32_t n_upper, const uint32_t* const* upper, const uint64_t* upper_n_) {
+    // Layer l holds PointIds [0, n_l) (lib.rs:275-281): n >= n_1 >= n_2 >= ... >= 1.  The descent carries ids found on layer l
+    // into layer l-1 and seeds PointId 0 on the top layer, so anything else would read adjacency rows out of bounds.
+    for (uint32_t l = 0; l < n_upper; ++l) {
+        const uint64_t below = l == 0 ? n_ : upper_n_[l - 1];
+        if (upper_n_[l] == 0 || upper_n_[l] > below)
+            return fail(IDB_ERR_INVALID_ARG, "layer %u has %llu nodes but the layer below has %llu (need n >= n_1 >= ... >= 1)", l + 1,
+                        (unsigned long long)upper_n_[l], (unsigned long long)below);
+    }
     n = n_;
     dim = dim_;
     M = M_;
@@ -380,6 +519,7 @@ idb_status Index::upload(const float* points, uint64_t n_, uint32_t dim_, uint32
     nchunks = (dim + 3) / 4;
     if (n == 0) return IDB_OK;
     const size_t stride = (size_t)nchunks * 4;
+    if (n > SIZE_MAX / (stride * sizeof(float)) || n > SIZE_MAX / (2 * (size_t)M * 4)) return fail(IDB_ERR_INVALID_ARG, "n * dim overflows size_t");
     CUDA_TRY(cudaMalloc(&d_points, n * stride * sizeof(float)));
     if (stride == dim) {
         CUDA_TRY(cudaMemcpyAsync(d_points, points, n * stride * sizeof(float), cudaMemcpyHostToDevice, stream));
@@ -415,6 +555,15 @@ idb_status Index::upload(const float* points, uint64_t n_, uint32_t dim_, uint32
         uint32_t bad = 0;
         cudaError_t e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess && bad == 0) {  // rows that list a PointId twice are legal input but rule out the b16 visited flavour
+            repeated_ids_kernel<<<num_sms * 8, 128, 0, stream>>>(d_zero, n, 2 * M, d_bad);
+            for (uint32_t l = 0; l < n_upper; ++l)
+                if (upper && upper[l] && upper_n_[l]) repeated_ids_kernel<<<num_sms * 8, 128, 0, stream>>>(d_upper[l], upper_n_[l], M, d_bad);
+            uint32_t rep = 0;
+            e = cudaMemcpyAsync(&rep, d_bad, 4, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            rows_distinct = rep == 0;
+        }
         cudaFree(d_bad);
         CUDA_TRY(e);
         if (bad) return fail(IDB_ERR_INVALID_ARG, "%u adjacency entries refer to PointIds outside their layer", bad);
@@ -492,33 +641,58 @@ idb_status idb_index_from_graph_bf16(const float* points, uint64_t n, uint32_t d
     return index_from_graph(points, n, dim, M, ef_search, zero, n_upper, upper, upper_n, device, true, out_index);
 }
 
-idb_status idb_search_batch_device(idb_index* index, const float* d_queries, uint64_t nq, uint32_t ef_search, uint32_t k,
-                                   uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len) {
-    if (!index) return fail(IDB_ERR_INVALID_ARG, "index is null");
-    Index* ix = reinterpret_cast<Index*>(index);
-    if (nq == 0) return IDB_OK;
-    if (!d_queries || !d_out_ids) return fail(IDB_ERR_INVALID_ARG, "queries/out_ids is null");
-    if (k == 0) return fail(IDB_ERR_INVALID_ARG, "k must be >= 1");
-    std::lock_guard<std::mutex> lk(ix->mu);
+}  // extern "C"
+
+namespace idb {
+static idb_status search_device_on_lane(Index* ix, Lane& ln, const float* d_queries, uint64_t nq, uint32_t ef_search, uint32_t k,
+                                        uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len, uint64_t* out_keys) {
     CUDA_TRY(cudaSetDevice(ix->device));
     const uint32_t ef = ef_search ? ef_search : ix->ef_search;
     if (ix->n == 0 || ef == 0) {  // empty index (core:359-361) / ef_search = 0: empty result lists
-        CUDA_TRY(fill_u32(d_out_ids, nq * k, kInvalid, ix->stream));
-        if (d_out_dist) CUDA_TRY(fill_u32(reinterpret_cast<uint32_t*>(d_out_dist), nq * k, 0x7f800000u, ix->stream));
-        if (d_out_len) CUDA_TRY(cudaMemsetAsync(d_out_len, 0, nq * 4, ix->stream));
-        ix->last_nq = 0;
+        CUDA_TRY(fill_u32(d_out_ids, nq * k, kInvalid, ln.stream));
+        if (d_out_dist) CUDA_TRY(fill_u32(reinterpret_cast<uint32_t*>(d_out_dist), nq * k, 0x7f800000u, ln.stream));
+        if (d_out_len) CUDA_TRY(cudaMemsetAsync(d_out_len, 0, nq * 4, ln.stream));
+        if (out_keys) CUDA_TRY(cudaMemsetAsync(out_keys, 0xFF, nq * k * 8, ln.stream));  // kKeyNone everywhere
+        ln.last_nq = 0;
         return IDB_OK;
     }
     const float* qp = d_queries;
     const size_t stride = (size_t)ix->nchunks * 4;
     if (stride != ix->dim || (reinterpret_cast<uintptr_t>(d_queries) & 15)) {
-        CUDA_TRY(ensure(ix->sc.q, ix->sc.q_cap, nq * stride));
-        CUDA_TRY(cudaMemsetAsync(ix->sc.q, 0, nq * stride * 4, ix->stream));
-        CUDA_TRY(cudaMemcpy2DAsync(ix->sc.q, stride * 4, d_queries, ix->dim * 4, ix->dim * 4, nq, cudaMemcpyDeviceToDevice,
-                                   ix->stream));
-        qp = ix->sc.q;
+        CUDA_TRY(ensure(ln.q, ln.q_cap, nq * stride));
+        CUDA_TRY(cudaMemsetAsync(ln.q, 0, nq * stride * 4, ln.stream));
+        CUDA_TRY(cudaMemcpy2DAsync(ln.q, stride * 4, d_queries, ix->dim * 4, ix->dim * 4, nq, cudaMemcpyDeviceToDevice, ln.stream));
+        qp = ln.q;
     }
-    return ix->enqueue_search(qp, nq, ef, k, d_out_ids, d_out_dist, d_out_len);
+    return ix->enqueue_search(ln, qp, nq, ef, k, d_out_ids, d_out_dist, d_out_len, out_keys);
+}
+
+// used by sharded.cu: lane 0, caller holds its mutex
+idb_status search_device_keys(Index* ix, Lane& ln, const float* d_queries, uint64_t nq, uint32_t ef_search, uint32_t k, uint32_t* d_ids,
+                              uint64_t* d_keys) {
+    return search_device_on_lane(ix, ln, d_queries, nq, ef_search, k, d_ids, nullptr, nullptr, d_keys);
+}
+}  // namespace idb
+
+extern "C" {
+
+idb_status idb_search_batch_device_lane(idb_index* index, uint32_t lane, const float* d_queries, uint64_t nq, uint32_t ef_search,
+                                        uint32_t k, uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len) {
+    if (!index) return fail(IDB_ERR_INVALID_ARG, "index is null");
+    Index* ix = reinterpret_cast<Index*>(index);
+    if (lane >= (uint32_t)kLanes) return fail(IDB_ERR_INVALID_ARG, "lane %u out of range (0..%d)", lane, kLanes - 1);
+    if (nq == 0) return IDB_OK;
+    if (!d_queries || !d_out_ids) return fail(IDB_ERR_INVALID_ARG, "queries/out_ids is null");
+    if (k == 0) return fail(IDB_ERR_INVALID_ARG, "k must be >= 1");
+    Lane& ln = ix->lanes[lane];
+    std::lock_guard<std::mutex> lk(ln.mu);
+    ix->last_lane.store((int)lane);
+    return search_device_on_lane(ix, ln, d_queries, nq, ef_search, k, d_out_ids, d_out_dist, d_out_len, nullptr);
+}
+
+idb_status idb_search_batch_device(idb_index* index, const float* d_queries, uint64_t nq, uint32_t ef_search, uint32_t k,
+                                   uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len) {
+    return idb_search_batch_device_lane(index, 0, d_queries, nq, ef_search, k, d_out_ids, d_out_dist, d_out_len);
 }
 
 idb_status idb_search_batch_f32(idb_index* index, const float* queries, uint64_t nq, uint32_t ef_search, uint32_t k,
@@ -528,50 +702,70 @@ idb_status idb_search_batch_f32(idb_index* index, const float* queries, uint64_t
     if (nq == 0) return IDB_OK;
     if (!queries || !out_ids) return fail(IDB_ERR_INVALID_ARG, "queries/out_ids is null");
     if (k == 0) return fail(IDB_ERR_INVALID_ARG, "k must be >= 1");
-    std::lock_guard<std::mutex> lk(ix->mu);
-    CUDA_TRY(cudaSetDevice(ix->device));
     const uint32_t ef = ef_search ? ef_search : ix->ef_search;
     if (ix->n == 0 || ef == 0) {
         for (uint64_t i = 0; i < nq * k; ++i) out_ids[i] = IDB_INVALID;
         if (out_dist) for (uint64_t i = 0; i < nq * k; ++i) out_dist[i] = INFINITY;
         if (out_len) std::memset(out_len, 0, nq * 4);
-        ix->last_nq = 0;
         return IDB_OK;
     }
+    // Hnsw<P>: Sync (core:352-356): any number of host threads may search at once; each call takes an idle lane (own stream and
+    // control state), so concurrent callers overlap on the device instead of serialising.
+    Lane& ln = ix->pick_lane();
+    std::lock_guard<std::mutex> lk(ln.mu, std::adopt_lock);
+    ix->last_lane.store((int)(&ln - ix->lanes));
+    CUDA_TRY(cudaSetDevice(ix->device));
     const size_t stride = (size_t)ix->nchunks * 4;
-    CUDA_TRY(ensure(ix->sc.q, ix->sc.q_cap, nq * stride));
-    CUDA_TRY(ensure(ix->sc.ids, ix->sc.ids_cap, nq * k));
-    CUDA_TRY(ensure(ix->sc.dist, ix->sc.dist_cap, nq * k));
-    CUDA_TRY(ensure(ix->sc.len, ix->sc.len_cap, nq));
+    CUDA_TRY(ensure(ln.q, ln.q_cap, nq * stride));
+    CUDA_TRY(ensure(ln.ids, ln.ids_cap, nq * k));
+    CUDA_TRY(ensure(ln.dist, ln.dist_cap, nq * k));
+    CUDA_TRY(ensure(ln.len, ln.len_cap, nq));
     if (stride == ix->dim) {
-        CUDA_TRY(cudaMemcpyAsync(ix->sc.q, queries, nq * stride * 4, cudaMemcpyHostToDevice, ix->stream));
+        CUDA_TRY(cudaMemcpyAsync(ln.q, queries, nq * stride * 4, cudaMemcpyHostToDevice, ln.stream));
     } else {
-        CUDA_TRY(cudaMemsetAsync(ix->sc.q, 0, nq * stride * 4, ix->stream));
-        CUDA_TRY(cudaMemcpy2DAsync(ix->sc.q, stride * 4, queries, ix->dim * 4, ix->dim * 4, nq, cudaMemcpyHostToDevice, ix->stream));
+        CUDA_TRY(cudaMemsetAsync(ln.q, 0, nq * stride * 4, ln.stream));
+        CUDA_TRY(cudaMemcpy2DAsync(ln.q, stride * 4, queries, ix->dim * 4, ix->dim * 4, nq, cudaMemcpyHostToDevice, ln.stream));
     }
-    idb_status st = ix->enqueue_search(ix->sc.q, nq, ef, k, ix->sc.ids, ix->sc.dist, ix->sc.len);
+    idb_status st = ix->enqueue_search(ln, ln.q, nq, ef, k, ln.ids, ln.dist, ln.len, nullptr);
     if (st != IDB_OK) return st;
-    CUDA_TRY(cudaMemcpyAsync(out_ids, ix->sc.ids, nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
-    if (out_dist) CUDA_TRY(cudaMemcpyAsync(out_dist, ix->sc.dist, nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
-    if (out_len) CUDA_TRY(cudaMemcpyAsync(out_len, ix->sc.len, nq * 4, cudaMemcpyDeviceToHost, ix->stream));
+    CUDA_TRY(cudaMemcpyAsync(out_ids, ln.ids, nq * k * 4, cudaMemcpyDeviceToHost, ln.stream));
+    if (out_dist) CUDA_TRY(cudaMemcpyAsync(out_dist, ln.dist, nq * k * 4, cudaMemcpyDeviceToHost, ln.stream));
+    if (out_len) CUDA_TRY(cudaMemcpyAsync(out_len, ln.len, nq * 4, cudaMemcpyDeviceToHost, ln.stream));
     uint32_t ctrl[16];
-    CUDA_TRY(cudaMemcpyAsync(ctrl, ix->sc.ctrl, 64, cudaMemcpyDeviceToHost, ix->stream));
-    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctrl, ln.ctrl, 64, cudaMemcpyDeviceToHost, ln.stream));
+    CUDA_TRY(cudaStreamSynchronize(ln.stream));
     if (ctrl[12] != 0)  // failures that survived the retry pass
         return fail(IDB_ERR_CAPACITY, "%u of %llu queries overflowed an internal per-query structure (visited table / tie list)",
                     ctrl[12], (unsigned long long)nq);
     return IDB_OK;
 }
 
+idb_status idb_last_search_failures(idb_index* index, uint32_t lane, uint32_t* out_failed) {
+    if (!index || !out_failed) return fail(IDB_ERR_INVALID_ARG, "null argument");
+    Index* ix = reinterpret_cast<Index*>(index);
+    if (lane >= (uint32_t)kLanes) return fail(IDB_ERR_INVALID_ARG, "lane %u out of range", lane);
+    Lane& ln = ix->lanes[lane];
+    std::lock_guard<std::mutex> lk(ln.mu);
+    *out_failed = 0;
+    if (!ln.ctrl || ln.last_nq == 0) return IDB_OK;
+    CUDA_TRY(cudaSetDevice(ix->device));
+    uint32_t ctrl[16];
+    CUDA_TRY(cudaMemcpyAsync(ctrl, ln.ctrl, 64, cudaMemcpyDeviceToHost, ln.stream));
+    CUDA_TRY(cudaStreamSynchronize(ln.stream));
+    *out_failed = ctrl[12];
+    return IDB_OK;
+}
+
 idb_status idb_last_search_counters(idb_index* index, uint64_t nq, uint64_t* out) {
     if (!index || !out) return fail(IDB_ERR_INVALID_ARG, "null argument");
     Index* ix = reinterpret_cast<Index*>(index);
-    std::lock_guard<std::mutex> lk(ix->mu);
-    if (nq > ix->last_nq) return fail(IDB_ERR_INVALID_ARG, "nq exceeds the last search batch (%llu)", (unsigned long long)ix->last_nq);
+    Lane& ln = ix->lanes[ix->last_lane.load()];
+    std::lock_guard<std::mutex> lk(ln.mu);
+    if (nq > ln.last_nq) return fail(IDB_ERR_INVALID_ARG, "nq exceeds the last search batch (%llu)", (unsigned long long)ln.last_nq);
     CUDA_TRY(cudaSetDevice(ix->device));
     std::vector<uint32_t> tmp(nq * 4);
-    CUDA_TRY(cudaMemcpyAsync(tmp.data(), ix->sc.counters, nq * 16, cudaMemcpyDeviceToHost, ix->stream));
-    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), ln.counters, nq * 16, cudaMemcpyDeviceToHost, ln.stream));
+    CUDA_TRY(cudaStreamSynchronize(ln.stream));
     for (uint64_t i = 0; i < nq * 4; ++i) out[i] = tmp[i];
     return IDB_OK;
 }
@@ -628,35 +822,52 @@ idb_status idb_index_export_upper(const idb_index* index, uint32_t layer, uint32
 idb_status idb_index_set_profiling(idb_index* index, int32_t enabled) {
     if (!index) return fail(IDB_ERR_INVALID_ARG, "index is null");
     Index* ix = reinterpret_cast<Index*>(index);
-    std::lock_guard<std::mutex> lk(ix->mu);
-    CUDA_TRY(cudaSetDevice(ix->device));
-    if (enabled && !ix->ev0) {
-        CUDA_TRY(cudaEventCreate(&ix->ev0));
-        CUDA_TRY(cudaEventCreate(&ix->ev1));
-    }
-    ix->profiling = enabled != 0;
+    ix->profiling = enabled != 0;  // the events are created by the next call on each lane
     return IDB_OK;
 }
 
 idb_status idb_index_last_kernel_ms(idb_index* index, float* out_ms, uint32_t* out_launches) {
     if (!index || !out_ms) return fail(IDB_ERR_INVALID_ARG, "null argument");
     Index* ix = reinterpret_cast<Index*>(index);
-    std::lock_guard<std::mutex> lk(ix->mu);
-    if (!ix->profiling || !ix->ev0) return fail(IDB_ERR_INVALID_ARG, "profiling is not enabled on this index");
+    Lane& ln = ix->lanes[ix->last_lane.load()];
+    std::lock_guard<std::mutex> lk(ln.mu);
+    if (!ix->profiling || !ln.ev0) return fail(IDB_ERR_INVALID_ARG, "profiling is not enabled on this index");
     CUDA_TRY(cudaSetDevice(ix->device));
-    CUDA_TRY(cudaEventSynchronize(ix->ev1));
-    CUDA_TRY(cudaEventElapsedTime(out_ms, ix->ev0, ix->ev1));
-    if (out_launches) *out_launches = ix->last_launches;
+    CUDA_TRY(cudaEventSynchronize(ln.ev1));
+    CUDA_TRY(cudaEventElapsedTime(out_ms, ln.ev0, ln.ev1));
+    if (out_launches) *out_launches = ln.last_launches;
     return IDB_OK;
 }
 
 void* idb_index_stream(idb_index* index) { return index ? reinterpret_cast<Index*>(index)->stream : nullptr; }
+uint32_t idb_index_num_lanes(void) { return (uint32_t)kLanes; }
+void* idb_index_lane_stream(idb_index* index, uint32_t lane) {
+    return index && lane < (uint32_t)kLanes ? reinterpret_cast<Index*>(index)->lanes[lane].stream : nullptr;
+}
 
 idb_status idb_index_sync(idb_index* index) {
     if (!index) return fail(IDB_ERR_INVALID_ARG, "index is null");
     Index* ix = reinterpret_cast<Index*>(index);
     CUDA_TRY(cudaSetDevice(ix->device));
-    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    for (auto& ln : ix->lanes) CUDA_TRY(cudaStreamSynchronize(ln.stream));
+    return IDB_OK;
+}
+
+idb_status idb_device_set_persisting_l2(int32_t device, int32_t enabled) {
+    if (device < 0 || device >= 64) return fail(IDB_ERR_INVALID_ARG, "device %d out of range", device);
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    g_l2_pref[device] = enabled ? 0 : -1;
+    if (g_ctx[device]) {
+        std::lock_guard<std::mutex> lk2(g_ctx[device]->mu);
+        g_ctx[device]->l2_allowed = enabled != 0;
+        if (!enabled && g_ctx[device]->l2_reserved) {
+            CUDA_TRY(cudaSetDevice(device));
+            CUDA_TRY(cudaDeviceSynchronize());
+            cudaCtxResetPersistingL2Cache();
+            CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));
+            g_ctx[device]->l2_reserved = 0;
+        }
+    }
     return IDB_OK;
 }
 

@@ -139,12 +139,17 @@ struct BuildScratch {
     uint64_t* sorted = nullptr;
     uint32_t* seg_start = nullptr;
     uint32_t* status = nullptr;
+    uint32_t* fail_list = nullptr;
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0;
-    unsigned char* ctrl = nullptr;  // [0..8) KA work counter, [8..16) relink work counter, [16..20) n_seg, [32..36) fail count (never reset)
+    // [0..8) KA work counter, [8..16) relink work counter, [16..20) n_seg, [20..24) KA fail count, [24..32) KA-retry work counter
+    // (all reset per batch); [32..36) inserts that failed even in the retry pass (never reset)
+    unsigned char* ctrl = nullptr;
+    uint32_t* h_fail = nullptr;     // pinned
     ~BuildScratch() {
         cudaFree(cand_keys); cudaFree(cand_cnt); cudaFree(pairs); cudaFree(sorted); cudaFree(seg_start); cudaFree(status);
-        cudaFree(cub_tmp); cudaFree(ctrl);
+        cudaFree(fail_list); cudaFree(cub_tmp); cudaFree(ctrl);
+        if (h_fail) cudaFreeHost(h_fail);
     }
 };
 
@@ -229,12 +234,12 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
     CUDA_TRY(cudaMalloc(&bs.sorted, (size_t)max_batch * cap * 8));
     CUDA_TRY(cudaMalloc(&bs.seg_start, (size_t)max_batch * cap * 4));
     CUDA_TRY(cudaMalloc(&bs.status, (size_t)max_batch * 4));
+    CUDA_TRY(cudaMalloc(&bs.fail_list, (size_t)max_batch * 4));
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&bs.h_fail), 4, cudaHostAllocDefault));
     CUDA_TRY(cudaMalloc(&bs.ctrl, 64));
     CUDA_TRY(cudaMemsetAsync(bs.ctrl, 0, 64, st));
     CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, bs.cub_bytes, bs.pairs, bs.sorted, (int)(max_batch * cap), 0, 64, st));
     CUDA_TRY(cudaMalloc(&bs.cub_tmp, std::max<size_t>(bs.cub_bytes, 16)));
-    idb_status s0 = ix->ensure_search_scratch(efc, max_batch, 1);
-    if (s0 != IDB_OK) return s0;
 
     const int ch = (int)((ix->nchunks + 31) / 32);
     // Staging the kept rows in shared memory (72 KB per 2-warp CTA -> 6 warps per SM) measured 1.4x SLOWER than reading them
@@ -255,12 +260,8 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
     a.cand_cnt = bs.cand_cnt;
     a.pairs = bs.pairs;
     a.status = bs.status;
-    a.fail_count = reinterpret_cast<uint32_t*>(bs.ctrl + 32);
-    a.vis_tables = ix->sc.vis_tables;
-    a.gslots = ix->sc.gslots;
-    a.vis_stride = ix->sc.vis_stride;
-    a.gshift = 32 - (uint32_t)std::log2((double)ix->sc.gslots);
-    a.tie_tables = ix->sc.tie_tables;
+    a.fail_count = reinterpret_cast<uint32_t*>(bs.ctrl + 20);
+    a.fail_list = bs.fail_list;
     a.sorted_pairs = bs.sorted;
     a.seg_start = bs.seg_start;
     a.n_seg = reinterpret_cast<uint32_t*>(bs.ctrl + 16);
@@ -278,8 +279,9 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
             a.count = (uint32_t)b;
             a.layer = layer;
             a.n_pairs_cap = (uint32_t)(b * cap);
-            CUDA_TRY(cudaMemsetAsync(bs.ctrl, 0, 24, st));
-            // KA: descent of every insert
+            CUDA_TRY(cudaMemsetAsync(bs.ctrl, 0, 32, st));
+            // KA: descent of every insert, then (device-side, normally a no-op) a retry pass with 2^21-slot hash sets and 64k-entry
+            // tie lists for the inserts whose per-warp structures overflowed (e.g. inside a cluster of thousands of duplicate vectors)
             BuildLaunch l;
             l.op = kOpInsertSearch;
             l.row_t = (int)((cap + 31) / 32);
@@ -287,8 +289,34 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
             l.stage = stage;
             l.smem_per_warp = k2_smem;
             l.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((b + kSearchWarps - 1) / kSearchWarps, (uint64_t)ix->search_grid()));
-            a.work_counter = reinterpret_cast<unsigned long long*>(bs.ctrl);
-            CUDA_TRY(build_dispatch_any(ch, a, l, st));
+            {
+                std::lock_guard<std::mutex> lk(ix->ctx->mu);  // the pool's tables must not be regrown under these launches
+                SearchArgs tier;
+                idb_status ts = ix->select_visited_tier(efc, tier, l.win);
+                if (ts != IDB_OK) return ts;
+                a.pool = tier.pool;
+                a.gslots = tier.gslots;
+                a.gshift = tier.gshift;
+                a.vis_mode = tier.vis_mode;
+                a.b16_cap_ids = tier.b16_cap_ids;
+                a.work_counter = reinterpret_cast<unsigned long long*>(bs.ctrl);
+                CUDA_TRY(build_dispatch_any(ch, a, l, st));
+                BuildArgs r = a;
+                BuildLaunch lr = l;
+                r.work_list = bs.fail_list;
+                r.n_work_dev = a.fail_count;
+                r.fail_list = nullptr;
+                r.fail_count = reinterpret_cast<uint32_t*>(bs.ctrl + 32);
+                r.work_counter = reinterpret_cast<unsigned long long*>(bs.ctrl + 24);
+                r.pool = ix->ctx->retry_pool();
+                r.gslots = kRetrySlots;
+                r.gshift = 32 - 21;
+                r.vis_mode = kVisHash;
+                lr.grid = kRetryCtas;
+                lr.win = LaunchWindow();
+                CUDA_TRY(build_dispatch_any(ch, r, lr, st));
+            }
+            CUDA_TRY(cudaMemcpyAsync(bs.h_fail, bs.ctrl + 32, 4, cudaMemcpyDeviceToHost, st));
             // K2: neighbour selection for the new nodes, own rows, link requests
             if (p.heuristic) {
                 l.op = kOpSelectNew;
@@ -310,6 +338,10 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
             a.work_counter = reinterpret_cast<unsigned long long*>(bs.ctrl + 8);
             CUDA_TRY(build_dispatch_any(ch, a, l, st));
             g0 += b;
+            CUDA_TRY(cudaStreamSynchronize(st));  // fail fast: an insert that overflowed even the retry pass ends the build here
+            if (*bs.h_fail)
+                return fail(IDB_ERR_CAPACITY, "%u inserts overflowed an internal per-insert structure (visited table / tie list) in the batch ending at %llu",
+                            *bs.h_fail, (unsigned long long)g0);
             if (p.progress) p.progress(g0, n, p.progress_user);  // set_position (core:519-525)
         }
         if (layer != 0) {  // lib.rs:323-328
@@ -317,11 +349,8 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
             CUDA_TRY(cudaGetLastError());
         }
     }
-    uint32_t fails = 0;
-    CUDA_TRY(cudaMemcpyAsync(&fails, bs.ctrl + 32, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (p.progress) p.progress(n, n, p.progress_user);  // finish (core:331-334)
-    if (fails) return fail(IDB_ERR_CAPACITY, "%u inserts overflowed an internal per-insert structure (visited table / tie list)", fails);
     return IDB_OK;
 }
 
@@ -338,8 +367,8 @@ extern "C" idb_status idb_build_f32(const float* rows, uint64_t n, uint32_t dim,
     if (n && !rows) return fail(IDB_ERR_INVALID_ARG, "rows is null");
     if (params->M < 2 || params->M > 64) return fail(IDB_ERR_INVALID_ARG, "M = %u unsupported (2..64)", params->M);
     if (n >= 0xFFFFFFFFull) return fail(IDB_ERR_INVALID_ARG, "N = %llu >= u32::MAX (lib.rs:256)", (unsigned long long)n);
-    if (params->ef_construction == 0 || params->ef_construction > 512)
-        return fail(IDB_ERR_UNSUPPORTED, "ef_construction = %u unsupported (1..512)", params->ef_construction);
+    if (params->ef_construction == 0 || params->ef_construction > 1024)
+        return fail(IDB_ERR_UNSUPPORTED, "ef_construction = %u unsupported (1..1024)", params->ef_construction);
     if (dim > 1024) return fail(IDB_ERR_UNSUPPORTED, "dim %u > 1024 is not supported yet", dim);
     if (!(params->ml > 0.0f) || params->ml >= 1.0f) return fail(IDB_ERR_INVALID_ARG, "ml must be in (0, 1)");
     if (params->storage != IDB_STORAGE_F32 && params->storage != IDB_STORAGE_BF16) return fail(IDB_ERR_INVALID_ARG, "unknown storage %u", params->storage);

@@ -12,17 +12,16 @@ struct BuildLaunch {
     bool stage;             // K2: kept rows staged in shared memory
     int grid;
     uint32_t smem_per_warp; // K2
+    LaunchWindow win;       // KA: persisting-L2 window on the b16 visited tables
 };
 
 template <int CH, int ROW_T, int EF_T, int B, class RT>
-cudaError_t launch_insert_search(const BuildArgs& a, int grid, cudaStream_t st) {
-    constexpr int kWarpBytes = 2 * 32 * EF_T * 8 + kSmallVisSlots * 4 + 128 * 4 + 128 * 8;
-    const int smem = kWarpBytes * kSearchWarps;
+cudaError_t launch_insert_search(const BuildArgs& a, const BuildLaunch& l, cudaStream_t st) {
+    const int smem = WarpSmem<EF_T>::kBytes * kSearchWarps;
     auto kern = insert_search_kernel<CH, ROW_T, EF_T, B, RT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, kSearchWarps * 32, smem, st>>>(a);
-    return cudaGetLastError();
+    return launch_with_window(kern, l.grid, kSearchWarps * 32, smem, st, l.win, a);
 }
 
 template <int CH, int NB, bool kStage, class RT>
@@ -47,11 +46,14 @@ cudaError_t build_dispatch_rt(const BuildArgs& a, const BuildLaunch& l, cudaStre
     switch (l.op) {
         case kOpInsertSearch:
             if (l.row_t <= 2) {
-                if (l.ef_t <= 4) return launch_insert_search<CH, 2, 4, B, RT>(a, l.grid, st);
-                return launch_insert_search<CH, 2, 16, B, RT>(a, l.grid, st);
+                if (l.ef_t <= 4) return launch_insert_search<CH, 2, 4, B, RT>(a, l, st);
+                if (l.ef_t <= 8) return launch_insert_search<CH, 2, 8, B, RT>(a, l, st);
+                if (l.ef_t <= 16) return launch_insert_search<CH, 2, 16, B, RT>(a, l, st);
+                return launch_insert_search<CH, 2, 32, B, RT>(a, l, st);
             }
-            if (l.ef_t <= 4) return launch_insert_search<CH, 4, 4, B, RT>(a, l.grid, st);
-            return launch_insert_search<CH, 4, 16, B, RT>(a, l.grid, st);
+            if (l.ef_t <= 4) return launch_insert_search<CH, 4, 4, B, RT>(a, l, st);
+            if (l.ef_t <= 16) return launch_insert_search<CH, 4, 16, B, RT>(a, l, st);
+            return launch_insert_search<CH, 4, 32, B, RT>(a, l, st);
         case kOpSelectNew:
         case kOpRelink:
             return l.stage ? launch_k2<CH, NB, true, RT>(a, l, st) : launch_k2<CH, NB, false, RT>(a, l, st);

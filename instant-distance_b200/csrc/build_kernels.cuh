@@ -14,7 +14,7 @@
 // target row (radix sort) and each target row is re-pruned once, by one warp, with all of its new candidates.  With
 // batch = 1 this is exactly the reference's sequential order; for any batch schedule the result is deterministic.
 #pragma once
-#include "internal.cuh"
+#include "search_kernel.cuh"
 
 namespace idb {
 
@@ -35,11 +35,14 @@ struct BuildArgs {
     uint64_t* pairs;                // count x 2M : (target << 32 | new), kKeyNone when unused
     uint32_t* status;               // count
     uint32_t* fail_count;
+    uint32_t* fail_list;            // KA: inserts whose visited table / tie list overflowed (null in the retry pass)
+    const uint32_t* work_list;      // retry pass: work item -> insert index of the batch
+    const uint32_t* n_work_dev;     // retry pass: number of work items, read on the device
     unsigned long long* work_counter;
-    uint32_t* vis_tables;
+    TablePool pool;                 // per-warp scratch tables, claimed per CTA (hnsw_device.cuh)
     uint32_t gslots, gshift;
-    uint32_t vis_stride;               // words between consecutive warps' tables (>= gslots)
-    uint64_t* tie_tables;
+    uint32_t vis_mode;
+    uint32_t b16_cap_ids;
     // relink
     const uint64_t* sorted_pairs;   // count*2M sorted ascending
     uint32_t n_pairs_cap;
@@ -166,34 +169,25 @@ struct SelectSmem {
 template <int CH, int ROW_T, int EF_T, int B, class RT>
 __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) insert_search_kernel(BuildArgs a) {  // same occupancy as K1
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_claim[2];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const uint32_t gwarp = blockIdx.x * kSearchWarps + warp;
-    constexpr int kNearBytes = 2 * 32 * EF_T * 8;
-    constexpr int kWarpBytes = kNearBytes + kSmallVisSlots * 4 + 128 * 4 + 128 * 8;
-    unsigned char* base = smem_raw + (size_t)warp * kWarpBytes;
+    const uint32_t n_work = a.n_work_dev ? *a.n_work_dev : a.count;
+    if (n_work == 0) return;  // the retry pass, normally
 
     WarpState s;
-    s.near_base = reinterpret_cast<uint64_t*>(base);
-    s.near_len = 32 * EF_T;
-    s.vis.small = reinterpret_cast<uint32_t*>(base + kNearBytes);
-    s.cpid = s.vis.small + kSmallVisSlots;
-    s.ckey = reinterpret_cast<uint64_t*>(s.cpid + 128);
-    s.vis.big = a.vis_tables + (size_t)gwarp * a.vis_stride;
-    s.vis.gslots = a.gslots;
-    s.vis.gshift = a.gshift;
-    s.vis.mode = kVisHash;
-    s.vis.count = 0;
-    s.vis.use_big = false;
-    s.ties = a.tie_tables + (size_t)gwarp * kTieCap;
+    WarpSmem<EF_T>::carve(s, smem_raw + (size_t)warp * WarpSmem<EF_T>::kBytes);
+    const uint32_t table0 = cta_tables_acquire(a.pool, s_claim, kSearchWarps);
+    bind_tables(s, a.pool, table0 + warp, a.gslots, a.gshift, a.vis_mode, a.b16_cap_ids);
     vis_clear_small(s.vis, lane);
 
     for (;;) {
-        unsigned long long w = 0;
-        if (lane == 0) w = atomicAdd(a.work_counter, 1ull);
-        w = __shfl_sync(kFullMask, w, 0);
-        if (w >= a.count) break;
-        const uint32_t neu = a.base + (uint32_t)w;
+        unsigned long long wi = 0;
+        if (lane == 0) wi = atomicAdd(a.work_counter, 1ull);
+        wi = __shfl_sync(kFullMask, wi, 0);
+        if (wi >= n_work) break;
+        const uint32_t w = a.work_list ? a.work_list[wi] : (uint32_t)wi;
+        const uint32_t neu = a.base + w;
         float4 q[CH];
         load_row<CH, RT>(a.g, neu, lane, q);
         descend<CH, ROW_T, EF_T, B, false, RT>(a.g, s, q, a.layer, a.efc, lane, nullptr);
@@ -203,10 +197,14 @@ __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) insert_se
         if (lane == 0) {
             a.cand_cnt[w] = len;
             a.status[w] = s.status;
-            if (s.status != kQueryOk) atomicAdd(a.fail_count, 1u);
+            if (s.status != kQueryOk) {
+                const uint32_t slot = atomicAdd(a.fail_count, 1u);
+                if (a.fail_list) a.fail_list[slot] = w;
+            }
         }
         finish_query(s, lane);
     }
+    cta_tables_release(a.pool, s_claim);
 }
 
 // ---------------------------------------------------------------------------------------------------------

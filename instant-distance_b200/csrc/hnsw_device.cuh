@@ -28,10 +28,11 @@ constexpr uint64_t kFlagExpanded = 1ull << 63;
 constexpr uint64_t kKeyMask = ~kFlagExpanded;
 constexpr uint64_t kKeyNone = ~0ull;          // sorts after every real key (real dist bits <= 0x7fc00000)
 constexpr int kSmallVisSlots = 512;           // shared-memory visited set used on the ef=1 layers
-constexpr int kTieCap = 1024;                 // per-warp tie list capacity (global memory)
+constexpr int kTieCap = 1024;                 // per-warp tie list capacity (global memory); the retry pool has kRetryTieCap
+constexpr int kRetryTieCap = 1 << 16;
 constexpr uint32_t kFullMask = 0xFFFFFFFFu;
 
-enum OptFlags : uint32_t { kOptPrefetchVectors = 1u, kOptPrefetchRows = 2u, kOptPrefetchNextRow = 8u, kOptFirstFreeSlot = 16u };
+enum OptFlags : uint32_t { kOptPrefetchVectors = 1u, kOptPrefetchRows = 2u, kOptPrefetchNextRow = 8u };
 
 enum QueryStatus : uint32_t { kQueryOk = 0, kQueryVisitedOverflow = 1, kQueryTieOverflow = 2 };
 
@@ -180,21 +181,26 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
 struct VisitedSet {
     uint32_t* small;   // shared
     uint32_t* big;     // global
-    uint32_t gslots;   // power of two
-    uint32_t gshift;   // 32 - log2(gslots)
+    uint32_t gslots;   // words in use: hash slots (power of two) / bitmap words / 8 * buckets (b16)
+    uint32_t gshift;   // hash flavour: 32 - log2(gslots)
     uint32_t count;
     bool use_big;
-    uint32_t mode;     // flavour of the big tier (VisMode).  A clean table is all ones (kInvalid) in every flavour;
-                       // gslots = words in use: hash slots (power of two) / bitmap words / bucket-set slots (power of two)
+    uint32_t mode;     // flavour of the big tier (VisMode).  A clean table is all ones (kInvalid) in every flavour
+    uint32_t nb;       // b16 flavour: buckets in use
+    float nb_inv;      // 1 / nb
+    uint32_t cap_ids;  // b16 flavour: ids the table may hold before the query is handed to the retry pass
+    uint32_t* hist;    // shared, 256 words: per-row slot bookkeeping of the b16 flavour (aliases WarpState::ckey, dead in that phase)
 };
 // Big-tier flavours, all exact:
-//   kVisHash    open addressing, one u32 slot per id, atomicCAS + linear probing (any n; used by the build and the retry pass)
+//   kVisHash    open addressing, one u32 slot per id, atomicCAS + linear probing (any n; the retry pass and the fallback)
 //   kVisBitmap  n bits, bit SET = not visited, one atomicAnd per id (n / 8 bytes per warp: DRAM resident)
-//   kVisBuckets 32-byte buckets of 8 ids, linear probing at bucket granularity.  ~1.25 slots per possible visited id, so the
-//               tables of all resident warps together fit the persisting part of L2 (K1's default when they do):
-//               a probe is ONE 32-byte read of an L2-resident sector instead of a read-modify-write of a random DRAM sector.
-enum VisMode : uint32_t { kVisHash = 0, kVisBitmap = 1, kVisBuckets = 2 };
-constexpr uint32_t kMaxBucketSteps = 128;  // buckets inspected per id before the query is handed to the retry pass (load <= 7/8: never in practice)
+//   kVisB16     32-byte buckets of 16 u16 slots, filled in order, NO atomics (the table is private to the warp and the warp
+//               arbitrates its own lanes with match/ballot).  slot = 15-bit tag | bit 15 "displaced by one bucket";
+//               (home bucket, tag) is an injective function of the PointId, so the set is exact for n <= buckets * 32768.
+//               ~2 slots per id a query can possibly visit: the tables of all resident warps together fit the persisting part
+//               of L2 (K1's and KA's default): a probe is ONE 32-byte read of an L2-resident sector, an insert one 2-byte
+//               store nobody waits for.
+enum VisMode : uint32_t { kVisHash = 0, kVisBitmap = 1, kVisB16 = 2 };
 
 __device__ __forceinline__ uint32_t vis_hash(uint32_t pid) { return pid * 0x9E3779B1u; }
 
@@ -218,15 +224,22 @@ __device__ __forceinline__ bool vis_insert_big(uint32_t* tab, uint32_t gshift, u
     }
 }
 
-// Bitmap flavour of the big tier (used when n / 32 words is no bigger than twice the hash table): one atomic per id,
-// no probe chains (with the hash set ~every row has at least one lane that needs a second, dependent probe), never overflows.
+// Bitmap flavour of the big tier: one atomic per id, no probe chains, never overflows.
 __device__ __forceinline__ uint32_t vis_bitmap_fetch_clear(uint32_t* tab, uint32_t pid) {
     return atomicAnd(tab + (pid >> 5), ~(1u << (pid & 31)));
 }
-// ---- bucket set ------------------------------------------------------------------------------------------
-// Invariant (no deletions): an id lives in the first bucket, starting from its home bucket, that had a free slot when it was
-// inserted; so a lookup that finds a free slot in a bucket without having found the id knows the id is absent.
+
+// ---- b16 bucket set --------------------------------------------------------------------------------------
+// Invariants (no deletions, slots of a bucket are filled in order 0..15):
+//   * an id lives in its home bucket if that bucket had a free slot when the id was inserted, else (flagged "displaced") in the
+//     next bucket; so "not in the home bucket, and the home bucket still has a free slot" proves absence with ONE 32-byte read;
+//   * the warp owns the table: concurrent inserts only ever come from lanes of this warp handling the same adjacency row, and
+//     those are arbitrated in registers (match_any on the home bucket + a 256-entry shared-memory tally for row entries that
+//     live in different registers), so inserts are plain stores and nobody waits for them.
+//   * PointIds within one adjacency row are distinct (true for every graph this library or the reference builds; adopted graphs
+//     are checked at upload and fall back to the atomic flavours if a row repeats an id).
 struct Bucket8 { uint4 lo, hi; };
+struct B16 { uint32_t home, tag; };
 __device__ __forceinline__ Bucket8 bucket_load(const uint32_t* tab, uint32_t b) {
     const uint4* p = reinterpret_cast<const uint4*>(tab + (size_t)b * 8);
     Bucket8 r;
@@ -234,37 +247,113 @@ __device__ __forceinline__ Bucket8 bucket_load(const uint32_t* tab, uint32_t b) 
     r.hi = __ldcg(p + 1);
     return r;
 }
-__device__ __forceinline__ uint32_t bucket_match(const Bucket8& k, uint32_t x) {  // bit i set <=> slot i == x
-    return (k.lo.x == x ? 1u : 0u) | (k.lo.y == x ? 2u : 0u) | (k.lo.z == x ? 4u : 0u) | (k.lo.w == x ? 8u : 0u) |
-           (k.hi.x == x ? 16u : 0u) | (k.hi.y == x ? 32u : 0u) | (k.hi.z == x ? 64u : 0u) | (k.hi.w == x ? 128u : 0u);
+__device__ __forceinline__ void b16_store(uint32_t* tab, uint32_t b, uint32_t pos, uint32_t val16) {
+    unsigned short* p = reinterpret_cast<unsigned short*>(tab) + ((size_t)b * 16 + pos);
+    asm volatile("st.global.cg.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)val16) : "memory");
 }
-__device__ __forceinline__ uint32_t bucket_home(const VisitedSet& v, uint32_t pid) { return vis_hash(pid) >> (v.gshift + 3); }
-// Visited::insert for one id given the snapshot `k` of its home bucket.  Returns true iff the id was not in the set.
-// *overflow is set if no free slot was found within kMaxBucketSteps buckets.
-__device__ __forceinline__ bool bucket_resolve(VisitedSet& v, uint32_t pid, uint32_t b, Bucket8 k, bool* overflow) {
-    const uint32_t bmask = (v.gslots >> 3) - 1;
-    for (uint32_t step = 0;; ++step) {
-        if (bucket_match(k, pid)) return false;
-        uint32_t em = bucket_match(k, kInvalid);
-        while (em) {  // claim a free slot of the snapshot; another lane of this warp may have taken it in the meantime
-            const uint32_t i = __ffs(em) - 1;
-            em &= em - 1;
-            const uint32_t old = atomicCAS(v.big + (size_t)b * 8 + i, kInvalid, pid);
-            if (old == kInvalid) return true;
-            if (old == pid) return false;  // the same id twice in one row: the other lane inserted it
+// (home bucket, 15-bit tag) of a PointId: tag = low 15 bits, home = (pid >> 15) + scramble(tag) mod nb.  Injective while
+// ceil(n / 32768) <= nb (checked on the host): given (home, tag) the group pid >> 15 is (home - scramble(tag)) mod nb.
+__device__ __forceinline__ B16 b16_of(const VisitedSet& v, uint32_t pid) {
+    B16 r;
+    r.tag = pid & 0x7FFFu;
+    const uint32_t x = (pid >> 15) + ((r.tag * 0x9E3779B1u) >> 10);  // < 2^17 + 2^22: exact in fp32
+    uint32_t q = (uint32_t)((float)x * v.nb_inv);
+    int32_t rem = (int32_t)(x - q * v.nb);
+    if (rem < 0) rem += (int32_t)v.nb;
+    if (rem >= (int32_t)v.nb) rem -= (int32_t)v.nb;
+    r.home = (uint32_t)rem;
+    return r;
+}
+// does any of the 16 halfwords equal val16?  (x - 0x00010001) & ~x & 0x80008000 is non-zero iff x has a zero halfword.
+__device__ __forceinline__ bool b16_has(const Bucket8& k, uint32_t val16) {
+    const uint32_t p = val16 | (val16 << 16);
+    const uint32_t w[8] = {k.lo.x, k.lo.y, k.lo.z, k.lo.w, k.hi.x, k.hi.y, k.hi.z, k.hi.w};
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t x = w[i] ^ p;
+        any |= (x - 0x00010001u) & ~x & 0x80008000u;
+    }
+    return any != 0;
+}
+// number of filled slots (slots fill in order, so the empty ones — 0xFFFF — are a suffix; with that invariant the halfword
+// zero test is exact for every halfword, not only the lowest)
+__device__ __forceinline__ uint32_t b16_count(const Bucket8& k) {
+    const uint32_t w[8] = {k.lo.x, k.lo.y, k.lo.z, k.lo.w, k.hi.x, k.hi.y, k.hi.z, k.hi.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t x = ~w[i];
+        m |= ((x - 0x00010001u) & ~x & 0x80008000u) >> i;  // bits 15-i and 31-i
+    }
+    return 16u - __popc(m);
+}
+// Exact insert by ONE lane on fresh data (the others wait): 1 inserted, 0 already there, 2 no room within two buckets.
+__device__ __forceinline__ uint32_t b16_insert_slow(VisitedSet& v, B16 t) {
+    uint32_t b = t.home, val = t.tag;
+    for (int step = 0;; ++step) {
+        const Bucket8 k = bucket_load(v.big, b);
+        if (b16_has(k, val)) return 0u;
+        const uint32_t cnt = b16_count(k);
+        if (cnt < 16u) {
+            b16_store(v.big, b, cnt, val);
+            atomicAdd(&v.hist[b & 255u], 1u);  // row entries in other registers hold an older snapshot of this bucket
+            return 1u;
         }
-        if (step + 1 >= kMaxBucketSteps) { *overflow = true; return false; }
-        b = (b + 1) & bmask;  // bucket full: the id, if present, is further along
-        k = bucket_load(v.big, b);
+        if (step == 1 || t.tag == 0x7FFFu) return 2u;  // 0x8000 | 0x7FFF is the EMPTY pattern: cannot be stored displaced
+        b = b + 1 == v.nb ? 0u : b + 1;
+        val = 0x8000u | t.tag;
     }
 }
-__device__ __forceinline__ bool vis_insert_big_any(VisitedSet& v, uint32_t pid) {
-    if (v.mode == kVisBitmap) return (vis_bitmap_fetch_clear(v.big, pid) >> (pid & 31)) & 1u;
-    if (v.mode == kVisBuckets) {
-        bool ovf = false;  // (callers insert a handful of ids into a table sized for thousands: cannot overflow)
-        const uint32_t b = bucket_home(v, pid);
-        return bucket_resolve(v, pid, b, bucket_load(v.big, b), &ovf);
+// Visited::insert (types.rs:32-40) for one id per lane, given the snapshot `bk` of its home bucket (loaded by the caller so that
+// the snapshots of a whole row are in flight together).  Warp-uniform call.  v.hist entries of the homes involved must have been
+// zeroed since the snapshots were taken (b16_tally_reset).  Returns true iff the id was not in the set; *ovf on overflow.
+__device__ __forceinline__ bool b16_commit(VisitedSet& v, B16 tg, const Bucket8& bk, bool want, int lane, bool* ovf) {
+    bool isnew = false, slow = false;
+    uint32_t cnt = 0;
+    if (want && !b16_has(bk, tg.tag)) {
+        cnt = b16_count(bk);
+        if (cnt >= 16u) slow = true;  // full: the id may live displaced in the next bucket
+        else isnew = true;
     }
+    const uint32_t peers = __match_any_sync(kFullMask, isnew ? tg.home : (0x80000000u | (uint32_t)lane));
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (isnew && lane == leader) base = atomicAdd(&v.hist[tg.home & 255u], (uint32_t)__popc(peers));
+    base = __shfl_sync(kFullMask, base, leader);
+    if (isnew) {
+        const uint32_t pos = cnt + base + __popc(peers & ((1u << lane) - 1u));
+        if (pos < 16u) b16_store(v.big, tg.home, pos, tg.tag);
+        else { isnew = false; slow = true; }
+    }
+    uint32_t sm = __ballot_sync(kFullMask, slow);
+    while (sm) {  // rare: one lane at a time, on fresh data
+        __syncwarp();  // orders the stores above / of the previous turn before this turn's loads
+        const int src = __ffs(sm) - 1;
+        sm &= sm - 1;
+        if (lane == src) {
+            const uint32_t r = b16_insert_slow(v, tg);
+            isnew = r == 1u;
+            if (r == 2u) *ovf = true;
+        }
+    }
+    __syncwarp();
+    return isnew;
+}
+__device__ __forceinline__ void b16_tally_reset(VisitedSet& v, B16 tg) { v.hist[tg.home & 255u] = 0u; }
+
+// One id per lane into the big tier, any flavour.  Warp-uniform call (the b16 flavour is cooperative).
+__device__ __forceinline__ bool vis_insert_big_any(VisitedSet& v, uint32_t pid, bool want, int lane, bool* ovf) {
+    if (v.mode == kVisB16) {
+        const B16 tg = b16_of(v, pid);
+        Bucket8 bk;
+        bk.lo = bk.hi = make_uint4(0u, 0u, 0u, 0u);
+        if (want) { bk = bucket_load(v.big, tg.home); b16_tally_reset(v, tg); }
+        __syncwarp();
+        return b16_commit(v, tg, bk, want, lane, ovf);
+    }
+    if (!want) return false;
+    if (v.mode == kVisBitmap) return (vis_bitmap_fetch_clear(v.big, pid) >> (pid & 31)) & 1u;
     return vis_insert_big(v.big, v.gshift, v.gslots - 1, pid);
 }
 
@@ -287,21 +376,22 @@ __device__ __forceinline__ void vis_clear(VisitedSet& v, int lane, bool next_big
     v.use_big = next_big;
 }
 __device__ __forceinline__ void vis_migrate_to_big(VisitedSet& v, int lane) {
+    bool ovf = false;  // (a few hundred ids into a table sized for thousands: cannot overflow)
 #pragma unroll 4
     for (int i = 0; i < kSmallVisSlots / 32; ++i) {
-        uint32_t x = v.small[lane + 32 * i];
-        if (x != kInvalid) vis_insert_big_any(v, x);
+        const uint32_t x = v.small[lane + 32 * i];
+        vis_insert_big_any(v, x, x != kInvalid, lane, &ovf);
     }
     __syncwarp();
     vis_clear_small(v, lane);
     v.use_big = true;
 }
 // Visited::insert (types.rs:32-40) for one id per lane, split in two so a lane can have the first probes of all its
-// row entries in flight before it waits for any of them:
+// row entries in flight before it waits for any of them (atomic flavours; the b16 flavour has its own row path):
 //   vis_probe  issues the first CAS and returns (old value, slot);  vis_settle follows the probe chain if needed.
-// Returns false for lanes with !want.  Caller guarantees capacity via vis_reserve.
+// Returns false for lanes with !want.  Caller guarantees capacity via vis_reserve.  Warp-uniform calls.
 struct VisProbe { uint32_t old, h; };
-__device__ __forceinline__ VisProbe vis_probe(VisitedSet& v, uint32_t pid, bool want) {
+__device__ __forceinline__ VisProbe vis_probe(VisitedSet& v, uint32_t pid, bool want, int lane) {
     VisProbe r;
     r.old = 0u;
     if (v.use_big && v.mode == kVisBitmap) {
@@ -309,9 +399,10 @@ __device__ __forceinline__ VisProbe vis_probe(VisitedSet& v, uint32_t pid, bool 
         if (want) r.old = vis_bitmap_fetch_clear(v.big, pid);
         return r;
     }
-    if (v.use_big && v.mode == kVisBuckets) {  // (rows go through visited_row_buckets; this serves cull / the seed)
+    if (v.use_big && v.mode == kVisB16) {  // (rows take their own path in search_layer; this serves cull / the seed)
+        bool ovf = false;                  // a handful of ids into an empty table: cannot overflow
         r.h = 0u;
-        if (want) r.old = vis_insert_big_any(v, pid) ? 1u : 0u;
+        r.old = vis_insert_big_any(v, pid, want, lane, &ovf) ? 1u : 0u;
         return r;
     }
     r.h = v.use_big ? (vis_hash(pid) >> v.gshift) : (vis_hash(pid) >> (32 - 9));
@@ -321,7 +412,7 @@ __device__ __forceinline__ VisProbe vis_probe(VisitedSet& v, uint32_t pid, bool 
 __device__ __forceinline__ bool vis_settle(VisitedSet& v, uint32_t pid, bool want, VisProbe r) {
     if (!want) return false;
     if (v.use_big && v.mode == kVisBitmap) return (r.old >> (pid & 31)) & 1u;
-    if (v.use_big && v.mode == kVisBuckets) return r.old != 0u;
+    if (v.use_big && v.mode == kVisB16) return r.old != 0u;
     uint32_t* tab = v.use_big ? v.big : v.small;
     const uint32_t mask = v.use_big ? v.gslots - 1 : (uint32_t)(kSmallVisSlots - 1);
     uint32_t old = r.old, h = r.h;
@@ -332,15 +423,15 @@ __device__ __forceinline__ bool vis_settle(VisitedSet& v, uint32_t pid, bool wan
         old = atomicCAS(tab + h, kInvalid, pid);
     }
 }
-__device__ __forceinline__ bool vis_insert(VisitedSet& v, uint32_t pid, bool want) {
-    return vis_settle(v, pid, want, vis_probe(v, pid, want));
+__device__ __forceinline__ bool vis_insert(VisitedSet& v, uint32_t pid, bool want, int lane) {
+    return vis_settle(v, pid, want, vis_probe(v, pid, want, lane));
 }
-// Make room for `incoming` more ids.  Returns false if the big table would exceed 3/4 load (query is aborted
-// with kQueryVisitedOverflow and retried by the host with a larger table).
+// Make room for `incoming` more ids.  Returns false if the big table would get too full (the query is aborted with
+// kQueryVisitedOverflow and re-run by the retry pass with a 2^21-slot hash set).
 __device__ __forceinline__ bool vis_reserve(VisitedSet& v, uint32_t incoming, int lane) {
     if (!v.use_big && v.count + incoming > kSmallVisSlots / 2) vis_migrate_to_big(v, lane);
     if (v.use_big && v.mode == kVisHash && v.count + incoming > (v.gslots / 4) * 3) return false;
-    if (v.use_big && v.mode == kVisBuckets && v.count + incoming > (v.gslots / 8) * 7) return false;
+    if (v.use_big && v.mode == kVisB16 && v.count + incoming > v.cap_ids) return false;
     return true;
 }
 
@@ -352,7 +443,8 @@ struct WarpState {
     uint32_t near_len;       // 32*EF_T
     uint32_t* cpid;          // shared: 128 compacted new ids of the current row
     uint64_t* ckey;          // shared: their 128 keys (canonical distance bits << 32 | pid)
-    uint64_t* ties;          // global: kTieCap keys
+    uint64_t* ties;          // global: tie_cap keys
+    uint32_t tie_cap;
     int cur;                 // live near buffer
     uint32_t cnt;            // len(nearest)
     uint32_t ntie;
@@ -446,7 +538,7 @@ __device__ __forceinline__ void collect_ties(WarpState& s, const uint64_t* old_n
         uint32_t m = __ballot_sync(kFullMask, tie);
         if (m) {
             uint32_t pos = s.ntie + __popc(m & ((1u << lane) - 1));
-            if (tie && pos < kTieCap) s.ties[pos] = k;
+            if (tie && pos < s.tie_cap) s.ties[pos] = k;
             s.ntie += __popc(m);
         }
     }
@@ -470,11 +562,11 @@ __device__ __forceinline__ void collect_ties(WarpState& s, const uint64_t* old_n
         uint32_t m = __ballot_sync(kFullMask, tie);
         if (m) {
             uint32_t pos = s.ntie + __popc(m & ((1u << lane) - 1));
-            if (tie && pos < kTieCap) s.ties[pos] = keyg[g];
+            if (tie && pos < s.tie_cap) s.ties[pos] = keyg[g];
             s.ntie += __popc(m);
         }
     }
-    if (s.ntie > kTieCap) { s.status = kQueryTieOverflow; s.ntie = kTieCap; }
+    if (s.ntie > s.tie_cap) { s.status = kQueryTieOverflow; s.ntie = s.tie_cap; }
     __threadfence_block();
     __syncwarp();
 }
@@ -519,7 +611,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
         if (seed_entry) {
             // push(PointId(0)) (lib.rs:364 / 444): the entry point is the only "row entry" of a pseudo expansion
             seed_entry = false;
-            vis_insert(s.vis, 0u, lane == 0);
+            vis_insert(s.vis, 0u, lane == 0, lane);
             s.vis.count = 1;
             if (lane == 0) s.cpid[0] = 0u;
             n_new = 1;
@@ -578,42 +670,22 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
 
             // ---- visited.insert for every row entry (lib.rs:705), compacted in row order ------------------
             if (!vis_reserve(s.vis, count, lane)) { s.status = kQueryVisitedOverflow; break; }
-            if (s.vis.use_big && s.vis.mode == kVisBuckets) {
-                // all home buckets of the row in flight at once (one 32-byte sector each), then resolve
+            if (s.vis.use_big && s.vis.mode == kVisB16) {
+                // all home buckets of the row in flight at once (one 32-byte sector each); the inserts are plain stores
+                // arbitrated inside the warp, so the row costs ONE L2 round trip and nothing waits for the stores
                 Bucket8 bk[ROW_T];
-                uint32_t hb[ROW_T];
+                B16 tg[ROW_T];
 #pragma unroll
                 for (int t = 0; t < ROW_T; ++t) {
-                    hb[t] = bucket_home(s.vis, ent[t]);
-                    if ((uint32_t)(lane + 32 * t) < count) bk[t] = bucket_load(s.vis.big, hb[t]);
+                    tg[t] = b16_of(s.vis, ent[t]);
+                    bk[t].lo = bk[t].hi = make_uint4(0u, 0u, 0u, 0u);
+                    if ((uint32_t)(lane + 32 * t) < count) { bk[t] = bucket_load(s.vis.big, tg[t].home); b16_tally_reset(s.vis, tg[t]); }
                 }
-                // common case per id: not in its home bucket and the bucket has a free slot -> claim it.  The claims of all of a
-                // lane's ids are issued before any result is looked at (one L2 round trip for the row, not one per id).
-                uint32_t claim[ROW_T];   // result of the slot claim
-                uint32_t state[ROW_T];   // 0 visited / not a row entry, 1 claim in flight, 2 general path (full bucket)
-#pragma unroll
-                for (int t = 0; t < ROW_T; ++t) {
-                    state[t] = 0u;
-                    claim[t] = 0u;
-                    if ((uint32_t)(lane + 32 * t) < count && !bucket_match(bk[t], ent[t])) {
-                        const uint32_t em = bucket_match(bk[t], kInvalid);
-                        state[t] = em ? 1u : 2u;
-                        // ids that share a home bucket see the same free slots: spread their claims over them instead of all
-                        // taking the first one (a lost claim costs the whole warp two more L2 round trips).  The choice is a
-                        // function of the ID, not of the lane: the same id listed twice in a row must claim the same slot, so
-                        // that the atomicCAS lets it count once.
-                        uint32_t pick = __ffs(em) - 1;
-                        if (!(g.flags & kOptFirstFreeSlot)) pick = __fns(em, 0, (((ent[t] * 0x85EBCA6Bu) >> 29) * __popc(em) >> 3) + 1);
-                        if (em) claim[t] = atomicCAS(s.vis.big + (size_t)hb[t] * 8 + pick, kInvalid, ent[t]);
-                    }
-                }
+                __syncwarp();
                 bool ovf = false;
 #pragma unroll
                 for (int t = 0; t < ROW_T; ++t) {
-                    bool fresh = state[t] == 1u && claim[t] == kInvalid;
-                    // lost the slot to another id of this row, or the bucket was full: general path on a fresh snapshot
-                    if (state[t] == 2u || (state[t] == 1u && claim[t] != kInvalid && claim[t] != ent[t]))
-                        fresh = bucket_resolve(s.vis, ent[t], hb[t], bucket_load(s.vis.big, hb[t]), &ovf);
+                    const bool fresh = b16_commit(s.vis, tg[t], bk[t], (uint32_t)(lane + 32 * t) < count, lane, &ovf);
                     const uint32_t m = __ballot_sync(kFullMask, fresh);
                     if (fresh) s.cpid[n_new + __popc(m & lt_mask)] = ent[t];
                     n_new += __popc(m);
@@ -622,7 +694,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
             } else {
                 VisProbe probe[ROW_T];
 #pragma unroll
-                for (int t = 0; t < ROW_T; ++t) probe[t] = vis_probe(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count);
+                for (int t = 0; t < ROW_T; ++t) probe[t] = vis_probe(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count, lane);
 #pragma unroll
                 for (int t = 0; t < ROW_T; ++t) {
                     const bool fresh = vis_settle(s.vis, ent[t], (uint32_t)(lane + 32 * t) < count, probe[t]);
@@ -749,7 +821,7 @@ __device__ __forceinline__ void cull(WarpState& s, int lane, bool next_big) {
         bool have = idx < s.cnt;
         uint64_t k = have ? near[idx] : 0ull;
         if (have) near[idx] = k & kKeyMask;                 // every result is a candidate again
-        vis_insert(s.vis, key_pid(k), have);
+        vis_insert(s.vis, key_pid(k), have, lane);
     }
     s.vis.count = s.cnt;
     __syncwarp();
@@ -792,6 +864,55 @@ __device__ __forceinline__ void descend(const GraphView& g, WarpState& s, const 
         counters4[1] = up_dist;
         counters4[2] = s.n_expand;
         counters4[3] = s.n_dist;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-warp scratch tables (big visited tier, tie list) are a DEVICE-wide pool sized for the warps that can be resident at once
+// (SMs x CTA slots per SM x warps per CTA), shared by every index, stream and kernel of this library on the device: a CTA claims
+// a slot of the SM it runs on when it starts and returns it (tables clean) when it exits.  Any number of search / build kernels
+// may therefore be in flight together — the next batch's CTAs move in as the previous batch's drain — without each needing its
+// own ~75 MB of tables (which would no longer fit the persisting part of L2).
+// ---------------------------------------------------------------------------------------------------------
+struct TablePool {
+    uint32_t* slot_masks;     // [word]: bit i set = slot i taken
+    int32_t fixed_word;       // >= 0: claim from this word (the retry pool); < 0: from word %smid
+    uint32_t word_base;       // subtracted from the word when the table index is formed (retry pool: its word; else 0)
+    uint32_t slots_per_word;  // <= 32
+    uint32_t* vis_tables;     // (word * slots_per_word + slot) * kWarpsPerCta + warp  ->  vis_stride words
+    uint32_t vis_stride;
+    uint64_t* tie_tables;     // same index -> tie_cap keys
+    uint32_t tie_cap;
+};
+__device__ __forceinline__ uint32_t current_smid() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+// Block-uniform: returns the table index of warp 0 of this CTA (consecutive warps follow).  s_claim: 2 words of shared memory.
+__device__ __forceinline__ uint32_t cta_tables_acquire(const TablePool& tp, uint32_t* s_claim, uint32_t warps_per_cta) {
+    if (threadIdx.x == 0) {
+        const uint32_t word = tp.fixed_word >= 0 ? (uint32_t)tp.fixed_word : current_smid();
+        const uint32_t all = tp.slots_per_word >= 32u ? 0xFFFFFFFFu : ((1u << tp.slots_per_word) - 1u);
+        uint32_t bit;
+        for (;;) {
+            const uint32_t freeb = ~atomicOr(tp.slot_masks + word, 0u) & all;
+            if (!freeb) { __nanosleep(256); continue; }  // more co-resident CTAs than slots (a tuning variant): wait for one
+            bit = __ffs(freeb) - 1;
+            if (!(atomicOr(tp.slot_masks + word, 1u << bit) & (1u << bit))) break;
+        }
+        __threadfence();  // the previous holder's clean-up stores are visible before we touch the tables
+        s_claim[0] = word;
+        s_claim[1] = bit;
+    }
+    __syncthreads();
+    return ((s_claim[0] - tp.word_base) * tp.slots_per_word + s_claim[1]) * warps_per_cta;
+}
+__device__ __forceinline__ void cta_tables_release(const TablePool& tp, const uint32_t* s_claim) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAnd(tp.slot_masks + s_claim[0], ~(1u << s_claim[1]));
     }
 }
 

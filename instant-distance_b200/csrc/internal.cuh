@@ -1,8 +1,9 @@
-// internal.cuh — host-side index object and kernel argument blocks (not part of the public ABI).
+// internal.cuh — host-side index object, per-device shared context and kernel argument blocks (not part of the public ABI).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -14,9 +15,10 @@ namespace idb {
 
 constexpr int kSearchWarps = 4;        // warps (= live queries) per CTA
 constexpr int kSearchCtasPerSm = 4;    // resident CTAs per SM -> 16 live queries per SM, <= 128 registers per thread
-constexpr int kMaxCtasPerSm = 8;       // upper bound over the tuning variants (scratch is sized for it)
-constexpr int kRetryWarps = 32;        // warps of the (normally idle) overflow-retry pass
+constexpr int kMaxCtasPerSm = 8;       // upper bound for IDB_CTAS_PER_SM
+constexpr int kRetryCtas = 8;          // CTA slots of the (normally idle) overflow-retry pool -> 32 warps
 constexpr uint32_t kRetrySlots = 1u << 21;
+constexpr int kLanes = 4;              // submission lanes per index (own stream + per-call control state)
 
 extern thread_local char g_err[512];
 idb_status fail(idb_status st, const char* fmt, ...);
@@ -44,27 +46,62 @@ struct SearchArgs {
     unsigned long long* work_counter;
     uint32_t* fail_count;
     uint32_t* fail_list;               // may be null (retry pass)
-    uint32_t* vis_tables;
-    uint32_t gslots, gshift;           // words in use per warp / 32 - log2(gslots) (hash and bucket flavours: gslots is a power of two)
-    uint32_t vis_stride;               // words between consecutive warps' tables (>= gslots)
+    TablePool pool;                    // per-warp scratch tables, claimed per CTA (hnsw_device.cuh)
+    uint32_t gslots, gshift;           // big visited tier: words in use per warp / hash flavour: 32 - log2(gslots)
     uint32_t vis_mode;                 // flavour of the big visited tier (hnsw_device.cuh VisMode)
-    uint64_t* tie_tables;
+    uint32_t b16_cap_ids;              // b16 flavour: ids per query before the retry pass takes over
     uint64_t* out_keys;                // optional: nq x k packed (distance bits << 32 | id_map[pid]) for the sharded all-gather
     const uint32_t* id_map;            // optional: PointId -> caller's global row id
     int variant;                       // tuning variant of the kernel template (0 = default)
 };
 
-struct Scratch {
-    uint32_t* vis_tables = nullptr;
-    uint32_t gslots = 0;          // hash slots per warp (power of two)
-    uint32_t bm_words = 0;        // != 0: K1 may use the bitmap flavour with this many words per warp
-    uint32_t* bucket_tables = nullptr;  // bucket-set flavour: compact tables (bucket_slots words per warp) under a persisting-L2 window
-    uint32_t bucket_slots = 0;    // != 0: K1 uses the bucket-set flavour
-    uint32_t bucket_cap = 0;      // slots per warp the buffer was allocated for
-    uint32_t vis_stride = 0;      // words per warp actually allocated (>= gslots; >= bitmap words when the bitmap flavour is on)
-    uint32_t* retry_tables = nullptr;
-    uint64_t* tie_tables = nullptr;
-    unsigned char* ctrl = nullptr;
+// Persisting-L2 access-policy window attached to a launch (the b16 visited tables), or none.
+struct LaunchWindow {
+    void* base = nullptr;
+    size_t bytes = 0;
+    float hit_ratio = 1.0f;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// One per CUDA device, shared by every index on it (reference-counted): the pool of per-warp scratch tables (sized for the
+// warps that can be RESIDENT, not per index or per call), the retry pool, and the device's persisting-L2 reservation.
+// ---------------------------------------------------------------------------------------------------------
+struct DeviceCtx {
+    int device = 0;
+    int num_sms = 148;
+    int slots_per_sm = kSearchCtasPerSm;   // CTA slots per SM (IDB_CTAS_PER_SM)
+    std::mutex mu;                         // held while tables are (re)allocated and while a launch that uses them is enqueued
+    uint32_t* slot_masks = nullptr;        // num_sms words + 1 (the retry pool)
+    uint32_t n_tables = 0;                 // num_sms * slots_per_sm * kSearchWarps
+    // b16 tier: fixed stride per warp, a prefix of it in use per call
+    uint32_t* b16_tables = nullptr;
+    uint32_t b16_stride = 0;               // u32 words per warp
+    // atomic tiers (hash / bitmap): allocated on first use, regrown (device idle) when a call needs more
+    uint32_t* big_tables = nullptr;
+    uint32_t big_stride = 0;
+    uint32_t* retry_tables = nullptr;      // kRetryCtas * kSearchWarps tables of kRetrySlots words
+    uint64_t* tie_tables = nullptr;        // n_tables * kTieCap
+    uint64_t* retry_ties = nullptr;        // kRetryCtas * kSearchWarps * kRetryTieCap
+    int max_persist = 0, max_window = 0;
+    size_t l2_reserved = 0;                // current cudaLimitPersistingL2CacheSize set by this library
+    bool l2_allowed = true;                // idb_device_set_persisting_l2 / IDB_L2_PERSIST
+    int refs = 0;
+
+    static idb_status acquire(int device, DeviceCtx** out);
+    static void release(DeviceCtx* c);
+    idb_status ensure_big(uint32_t stride_words);          // caller holds mu
+    idb_status reserve_l2(size_t bytes);                    // caller holds mu
+    TablePool main_pool(bool b16) const;
+    TablePool retry_pool() const;
+    ~DeviceCtx();
+};
+
+// Per-call control state + host-API staging buffers; one per submission lane.  Calls on one lane are stream-ordered, so the
+// buffers are reused without waiting; calls on different lanes overlap on the device.
+struct Lane {
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    unsigned char* ctrl = nullptr;   // [0..8) K1 work counter, [16..20) K1 fail count, [32..40) retry work counter, [48..52) retry fail count
     uint32_t* status = nullptr;   size_t status_cap = 0;
     uint32_t* fail_list = nullptr; size_t fail_cap = 0;
     uint32_t* counters = nullptr; size_t counters_cap = 0;
@@ -77,13 +114,21 @@ struct Scratch {
     uint64_t* keys_all = nullptr;   size_t keys_all_cap = 0;
     float* q2 = nullptr;          size_t q2_cap = 0;
     uint32_t* ids2 = nullptr;     size_t ids2_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t last_nq = 0;
+    uint32_t last_launches = 0;
+    void free_all();
 };
 
 struct Index {
     int device = 0;
     int num_sms = 148;
-    cudaStream_t stream = nullptr;
-    std::mutex mu;
+    DeviceCtx* ctx = nullptr;
+    Lane lanes[kLanes];
+    cudaStream_t stream = nullptr;             // = lanes[0].stream: uploads, builds, the default lane
+    std::mutex mu;                             // graph-level operations (build, export, id map)
+    std::atomic<uint32_t> next_lane{0};        // host-API calls rotate over the lanes
+    std::atomic<int> last_lane{0};
 
     uint64_t n = 0;
     uint32_t dim = 0, nchunks = 0, M = 32, ef_search = 100;
@@ -95,22 +140,16 @@ struct Index {
     std::vector<uint64_t> upper_n;
     const uint32_t** d_upper_ptrs = nullptr;   // device copy of the pointer table
     uint32_t* d_id_map = nullptr;              // shard: PointId -> global row id (idb_index_set_id_map)
-    uint64_t* pending_out_keys = nullptr;      // set by the sharded path around enqueue_search
+    bool rows_distinct = true;                 // no adjacency row lists a PointId twice (checked for adopted graphs)
 
-    Scratch sc;
-    uint64_t last_nq = 0;
-    // tuning knobs (env IDB_OPT / IDB_VIS_MULT / IDB_VIS_BUCKETS / IDB_VIS_BITMAP / IDB_CTAS_PER_SM); none of them changes results
+    // tuning knobs (env IDB_OPT / IDB_VIS_MULT / IDB_VIS_TIER / IDB_B16_BYTES / IDB_VIS_SLOTS / IDB_VARIANT); none of them changes results
     uint32_t opt_flags = 0;       // L2 prefetch of rows/vectors: measured neutral-to-negative once 16 rows are in flight (profiles/r01_call4)
-    uint32_t vis_mult = 4;        // visited table slots = next_pow2(vis_mult * 2M * ef): load <= ~0.15, probe chains ~1
-    int ctas_per_sm = kSearchCtasPerSm;
-    uint32_t vis_slots_override = 0; // IDB_VIS_SLOTS (tests): exact per-warp visited-table size, to force the overflow -> retry path
-    int vis_bitmap = 1;           // IDB_VIS_BITMAP: 0 hash set, 1 bitmap over PointIds when it is no bigger than 2x the hash table
-    uint32_t bucket_slots_override = 0; // IDB_BUCKET_SLOTS (tests): exact per-warp bucket-set size
-    int vis_buckets = 1;          // IDB_VIS_BUCKETS: 1 = bucket set when the tables of all resident warps fit the persisting part of L2
+    uint32_t vis_mult = 4;        // hash flavour: slots = next_pow2(vis_mult * 2M * ef): load <= ~0.15, probe chains ~1
+    uint32_t vis_slots_override = 0; // IDB_VIS_SLOTS (tests): exact hash-table size, to force the overflow -> retry path
+    uint32_t b16_bytes_override = 0; // IDB_B16_BYTES (tests / sweeps): exact b16 table bytes per warp in use
+    int vis_tier = -1;            // IDB_VIS_TIER: -1 auto (b16 when exact for this n, else bitmap / hash), 0 hash, 1 bitmap, 2 b16
     int variant = 0;              // IDB_VARIANT: alternative (rows in flight, CTAs/SM) instantiations of K1
     bool profiling = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    uint32_t last_launches = 0;
 
     ~Index();
     idb_status init_device(int dev);
@@ -120,9 +159,13 @@ struct Index {
     idb_status narrow_points_to_bf16();                                  // d_points (f32) -> d_points_bf16, frees d_points
     idb_status copy_points_f32(float* host_out, uint64_t r0, uint64_t m);  // rows [r0, r0+m) as n x dim f32 on the host
     int search_grid() const;
-    idb_status ensure_search_scratch(uint32_t ef, uint64_t nq, uint32_t k);
-    idb_status enqueue_search(const float* d_queries_padded, uint64_t nq, uint32_t ef, uint32_t k, uint32_t* d_ids, float* d_dist,
-                              uint32_t* d_len);
+    // Fills the visited-tier fields of `a` (pool, gslots, ...) for a traversal with this ef and returns the launch window.
+    // Caller holds ctx->mu.
+    idb_status select_visited_tier(uint32_t ef, SearchArgs& a, LaunchWindow& win);
+    idb_status ensure_lane_scratch(Lane& ln, uint64_t nq);
+    idb_status enqueue_search(Lane& ln, const float* d_queries_padded, uint64_t nq, uint32_t ef, uint32_t k, uint32_t* d_ids,
+                              float* d_dist, uint32_t* d_len, uint64_t* out_keys);
+    Lane& pick_lane();
 };
 
 cudaError_t fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t st);

@@ -1,17 +1,17 @@
 // K1 instantiation for rows of up to 128 floats (1 float4 chunk(s) per lane, 16 row loads in flight per lane).
 #include "search_kernel.cuh"
 namespace idb {
-cudaError_t dispatch_search_ch1(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st) {
+cudaError_t dispatch_search_ch1(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st, const LaunchWindow& win) {
     // tuning variants of the headline shape (ROW_T=2, EF_T=4): rows in flight per lane x resident CTAs per SM
     if (a.variant && row_t <= 2 && ef_t <= 4) {
         switch (a.variant) {
-            case 1: return launch_search<1, 2, 4, 8, 5>(a, grid, st);
-            case 2: return launch_search<1, 2, 4, 8, 6>(a, grid, st);
-            case 3: return launch_search<1, 2, 4, 4, 8>(a, grid, st);
-            case 4: return launch_search<1, 2, 4, 16, 3>(a, grid, st);
+            case 1: return launch_search<1, 2, 4, 8, 5>(a, grid, st, win);
+            case 2: return launch_search<1, 2, 4, 8, 6>(a, grid, st, win);
+            case 3: return launch_search<1, 2, 4, 4, 8>(a, grid, st, win);
+            case 4: return launch_search<1, 2, 4, 16, 3>(a, grid, st, win);
             default: break;
         }
     }
-    return dispatch_row_ef<1, 16>(a, row_t, ef_t, grid, st);
+    return dispatch_row_ef<1, 16>(a, row_t, ef_t, grid, st, win);
 }
 }  // namespace idb

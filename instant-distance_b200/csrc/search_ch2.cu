@@ -1,7 +1,7 @@
 // K1 instantiation for rows of up to 256 floats (2 float4 chunk(s) per lane, 8 row loads in flight per lane).
 #include "search_kernel.cuh"
 namespace idb {
-cudaError_t dispatch_search_ch2(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st) {
-    return dispatch_row_ef<2, 8>(a, row_t, ef_t, grid, st);
+cudaError_t dispatch_search_ch2(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st, const LaunchWindow& win) {
+    return dispatch_row_ef<2, 8>(a, row_t, ef_t, grid, st, win);
 }
 }  // namespace idb

@@ -1,6 +1,8 @@
 // search_kernel.cuh — K1: batched Hnsw::search kernel (lib.rs:352-383 per query) and its launch helpers.
 // Instantiated once per CH (float4 chunks per lane) in search_chN.cu so the translation units build in parallel.
 #pragma once
+#include <cstring>
+
 #include "internal.cuh"
 
 namespace idb {
@@ -10,32 +12,50 @@ namespace idb {
 // ---------------------------------------------------------------------------------------------------------
 // FULL: dim is a multiple of 128, i.e. every lane owns a real chunk in each of its CH slots: no chunk predicates, and
 // full batches of row loads carry no predicates at all (hnsw_device.cuh batch_distances_impl).
+// Shared-memory carve-up of one traversal warp (K1 and the build's KA).
+template <int EF_T>
+struct WarpSmem {
+    static constexpr int kNearBytes = 2 * 32 * EF_T * 8;
+    static constexpr int kBytes = kNearBytes + kSmallVisSlots * 4 + 128 * 4 + 128 * 8;
+    static __device__ __forceinline__ void carve(WarpState& s, unsigned char* base) {
+        s.near_base = reinterpret_cast<uint64_t*>(base);
+        s.near_len = 32 * EF_T;
+        s.vis.small = reinterpret_cast<uint32_t*>(base + kNearBytes);
+        s.cpid = s.vis.small + kSmallVisSlots;
+        s.ckey = reinterpret_cast<uint64_t*>(s.cpid + 128);
+        s.vis.hist = reinterpret_cast<uint32_t*>(s.ckey);  // 256 words, only live between a row load and its distances
+    }
+};
+// Point the warp at its claimed scratch tables.
+__device__ __forceinline__ void bind_tables(WarpState& s, const TablePool& tp, uint32_t table, uint32_t gslots, uint32_t gshift,
+                                            uint32_t mode, uint32_t cap_ids) {
+    s.vis.big = tp.vis_tables + (size_t)table * tp.vis_stride;
+    s.vis.gslots = gslots;
+    s.vis.gshift = gshift;
+    s.vis.mode = mode;
+    s.vis.nb = gslots >> 3;
+    s.vis.nb_inv = 1.0f / (float)(gslots >> 3);
+    s.vis.cap_ids = cap_ids;
+    s.vis.count = 0;
+    s.vis.use_big = false;
+    s.ties = tp.tie_tables + (size_t)table * tp.tie_cap;
+    s.tie_cap = tp.tie_cap;
+}
+
 template <int CH, int ROW_T, int EF_T, int B, int OCC, class RT = RowF32, bool FULL = false>
 __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_claim[2];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const uint32_t gwarp = blockIdx.x * kSearchWarps + warp;
-
-    constexpr int kNearBytes = 2 * 32 * EF_T * 8;
-    constexpr int kWarpBytes = kNearBytes + kSmallVisSlots * 4 + 128 * 4 + 128 * 8;
-    unsigned char* base = smem_raw + (size_t)warp * kWarpBytes;
+    const unsigned long long n_work = a.n_work_dev ? (unsigned long long)*a.n_work_dev : a.n_work;
+    if (n_work == 0) return;  // the retry pass, normally: nothing to do, no tables claimed
 
     WarpState s;
-    s.near_base = reinterpret_cast<uint64_t*>(base);
-    s.near_len = 32 * EF_T;
-    s.vis.small = reinterpret_cast<uint32_t*>(base + kNearBytes);
-    s.cpid = s.vis.small + kSmallVisSlots;
-    s.ckey = reinterpret_cast<uint64_t*>(s.cpid + 128);
-    s.vis.big = a.vis_tables + (size_t)gwarp * a.vis_stride;
-    s.vis.gslots = a.gslots;
-    s.vis.gshift = a.gshift;
-    s.vis.mode = a.vis_mode;
-    s.vis.count = 0;
-    s.vis.use_big = false;
-    s.ties = a.tie_tables + (size_t)gwarp * kTieCap;
-    vis_clear_small(s.vis, lane);  // big tables are handed over clean by the host / previous launch
-    const unsigned long long n_work = a.n_work_dev ? (unsigned long long)*a.n_work_dev : a.n_work;
+    WarpSmem<EF_T>::carve(s, smem_raw + (size_t)warp * WarpSmem<EF_T>::kBytes);
+    const uint32_t table0 = cta_tables_acquire(a.pool, s_claim, kSearchWarps);
+    bind_tables(s, a.pool, table0 + warp, a.gslots, a.gshift, a.vis_mode, a.b16_cap_ids);
+    vis_clear_small(s.vis, lane);  // the big tables are handed over clean by their previous holder
 
     for (;;) {
         unsigned long long w = 0;
@@ -74,38 +94,63 @@ __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchAr
         }
         finish_query(s, lane);
     }
+    cta_tables_release(a.pool, s_claim);
+}
+
+// Launch with (optionally) a persisting-L2 access-policy window on the b16 visited tables as a LAUNCH attribute: no stream state.
+template <class Kern, class Args>
+static cudaError_t launch_with_window(Kern kern, int grid, int block, int smem, cudaStream_t stream, const LaunchWindow& win,
+                                      const Args& a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (win.base && win.bytes) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = win.base;
+        attr[0].val.accessPolicyWindow.num_bytes = win.bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = win.hit_ratio;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 template <int CH, int ROW_T, int EF_T, int B, int OCC = kSearchCtasPerSm, class RT = RowF32, bool FULL = false>
-static cudaError_t launch_search(const SearchArgs& a, int grid, cudaStream_t stream) {
-    constexpr int kWarpBytes = 2 * 32 * EF_T * 8 + kSmallVisSlots * 4 + 128 * 4 + 128 * 8;
-    const int smem = kWarpBytes * kSearchWarps;
+static cudaError_t launch_search(const SearchArgs& a, int grid, cudaStream_t stream, const LaunchWindow& win) {
+    const int smem = WarpSmem<EF_T>::kBytes * kSearchWarps;
     auto kern = search_kernel<CH, ROW_T, EF_T, B, OCC, RT, FULL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, kSearchWarps * 32, smem, stream>>>(a);
-    return cudaGetLastError();
+    return launch_with_window(kern, grid, kSearchWarps * 32, smem, stream, win, a);
 }
 
 template <int CH, int ROW_T, int EF_T, int B, class RT>
-cudaError_t launch_search_full(const SearchArgs& a, int grid, cudaStream_t st) {
-    if (a.g.nchunks == 32u * CH) return launch_search<CH, ROW_T, EF_T, B, kSearchCtasPerSm, RT, true>(a, grid, st);
-    return launch_search<CH, ROW_T, EF_T, B, kSearchCtasPerSm, RT, false>(a, grid, st);
+cudaError_t launch_search_full(const SearchArgs& a, int grid, cudaStream_t st, const LaunchWindow& win) {
+    if (a.g.nchunks == 32u * CH) return launch_search<CH, ROW_T, EF_T, B, kSearchCtasPerSm, RT, true>(a, grid, st, win);
+    return launch_search<CH, ROW_T, EF_T, B, kSearchCtasPerSm, RT, false>(a, grid, st, win);
 }
 template <int CH, int B, class RT>
-cudaError_t dispatch_row_ef_rt(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st) {
+cudaError_t dispatch_row_ef_rt(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st, const LaunchWindow& win) {
     if (row_t <= 2) {
-        if (ef_t <= 4) return launch_search_full<CH, 2, 4, B, RT>(a, grid, st);
-        return launch_search_full<CH, 2, 16, B, RT>(a, grid, st);
+        if (ef_t <= 4) return launch_search_full<CH, 2, 4, B, RT>(a, grid, st, win);
+        if (ef_t <= 8) return launch_search_full<CH, 2, 8, B, RT>(a, grid, st, win);
+        if (ef_t <= 16) return launch_search_full<CH, 2, 16, B, RT>(a, grid, st, win);
+        return launch_search_full<CH, 2, 32, B, RT>(a, grid, st, win);
     }
-    if (ef_t <= 4) return launch_search_full<CH, 4, 4, B, RT>(a, grid, st);
-    return launch_search_full<CH, 4, 16, B, RT>(a, grid, st);
+    if (ef_t <= 4) return launch_search_full<CH, 4, 4, B, RT>(a, grid, st, win);
+    if (ef_t <= 16) return launch_search_full<CH, 4, 16, B, RT>(a, grid, st, win);
+    return launch_search_full<CH, 4, 32, B, RT>(a, grid, st, win);
 }
 template <int CH, int B>
-cudaError_t dispatch_row_ef(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st) {
+cudaError_t dispatch_row_ef(const SearchArgs& a, int row_t, int ef_t, int grid, cudaStream_t st, const LaunchWindow& win) {
     // bf16 rows stay packed while in flight (half the registers per row): twice the rows in flight per lane
-    if (a.g.bf16) return dispatch_row_ef_rt<CH, (2 * B <= 16 ? 2 * B : B), RowBF16>(a, row_t, ef_t, grid, st);
-    return dispatch_row_ef_rt<CH, B, RowF32>(a, row_t, ef_t, grid, st);
+    if (a.g.bf16) return dispatch_row_ef_rt<CH, (2 * B <= 16 ? 2 * B : B), RowBF16>(a, row_t, ef_t, grid, st, win);
+    return dispatch_row_ef_rt<CH, B, RowF32>(a, row_t, ef_t, grid, st, win);
 }
 
 }  // namespace idb

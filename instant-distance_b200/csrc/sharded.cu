@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "internal.cuh"
@@ -162,6 +163,45 @@ idb_status idb_index_set_id_map(idb_index* index, const uint32_t* global_ids) {
     return IDB_OK;
 }
 
+}  // extern "C" (reopened below)
+
+namespace idb {
+idb_status search_device_keys(Index* ix, Lane& ln, const float* d_queries, uint64_t nq, uint32_t ef_search, uint32_t k, uint32_t* d_ids,
+                              uint64_t* d_keys);  // api.cu
+
+// Per-shard K1 (its epilogue packs (distance bits, global id) keys) -> ONE ncclAllGather -> merge kernel, all on lane 0's stream.
+// The caller holds lanes[0].mu.
+static idb_status sharded_search_locked(Index* ix, Comm* c, Lane& ln, const float* d_queries, uint64_t nq, uint32_t ef_search, uint32_t k,
+                                        uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len) {
+    CUDA_TRY(cudaSetDevice(ix->device));
+    // merge kernel: `wpb` warps per CTA, each with world * k keys in shared memory; check the launch BEFORE the collective is enqueued
+    int max_smem = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ix->device));
+    const size_t per_warp = (size_t)c->world * k * 8;
+    int wpb = 4;
+    while (wpb > 1 && per_warp * wpb > (size_t)max_smem) wpb >>= 1;
+    if (per_warp * wpb > (size_t)max_smem)
+        return fail(IDB_ERR_UNSUPPORTED, "world * k = %llu keys per query do not fit the merge kernel's shared memory (%d bytes)",
+                    (unsigned long long)c->world * k, max_smem);
+    const size_t per = (size_t)nq * k;
+    CUDA_TRY(ensure_u64(ln.keys_local, ln.keys_local_cap, per));
+    CUDA_TRY(ensure_u64(ln.keys_all, ln.keys_all_cap, per * c->world));
+    CUDA_TRY(ensure_u32(ln.ids, ln.ids_cap, per));
+    idb_status st = search_device_keys(ix, ln, d_queries, nq, ef_search, k, ln.ids, ln.keys_local);
+    if (st != IDB_OK) return st;
+    NCCL_TRY(nccl().AllGather(ln.keys_local, ln.keys_all, per, ncclUint64, c->comm, ln.stream));
+    const size_t smem = (size_t)wpb * per_warp;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::min<uint64_t>((nq + wpb - 1) / wpb, (uint64_t)ix->num_sms * 8);
+    merge_topk_kernel<<<grid, wpb * 32, smem, ln.stream>>>(ln.keys_all, (uint32_t)c->world, nq, k, d_out_ids, d_out_dist, d_out_len);
+    CUDA_TRY(cudaGetLastError());
+    ln.last_launches += 2;  // all-gather + merge
+    return IDB_OK;
+}
+}  // namespace idb
+
+extern "C" {
+
 // All device pointers; d_queries is nq x dim.  Collective: every rank of `comm` calls it with the same queries.
 idb_status idb_sharded_search_batch_device(idb_index* index, idb_comm* comm, const float* d_queries, uint64_t nq, uint32_t ef_search,
                                            uint32_t k, uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len) {
@@ -170,71 +210,37 @@ idb_status idb_sharded_search_batch_device(idb_index* index, idb_comm* comm, con
     Comm* c = reinterpret_cast<Comm*>(comm);
     if (nq == 0) return IDB_OK;
     if (!d_queries || !d_out_ids || k == 0) return fail(IDB_ERR_INVALID_ARG, "bad argument");
-    if ((uint64_t)c->world * k * 8 > 96 * 1024) return fail(IDB_ERR_UNSUPPORTED, "world * k = %u too large for the merge kernel", c->world * k);
-    std::lock_guard<std::mutex> lk(ix->mu);
-    CUDA_TRY(cudaSetDevice(ix->device));
-    const size_t per = (size_t)nq * k;
-    CUDA_TRY(ensure_u64(ix->sc.keys_local, ix->sc.keys_local_cap, per));
-    CUDA_TRY(ensure_u64(ix->sc.keys_all, ix->sc.keys_all_cap, per * c->world));
-    CUDA_TRY(ensure_u32(ix->sc.ids, ix->sc.ids_cap, per));
-    const uint32_t ef = ef_search ? ef_search : ix->ef_search;
-    if (ix->n == 0 || ef == 0) {
-        CUDA_TRY(cudaMemsetAsync(ix->sc.keys_local, 0xFF, per * 8, ix->stream));  // kKeyNone everywhere
-    } else {
-        const float* qp = d_queries;
-        const size_t stride = (size_t)ix->nchunks * 4;
-        if (stride != ix->dim || (reinterpret_cast<uintptr_t>(d_queries) & 15)) {
-            CUDA_TRY(ensure_f32(ix->sc.q, ix->sc.q_cap, nq * stride));
-            CUDA_TRY(cudaMemsetAsync(ix->sc.q, 0, nq * stride * 4, ix->stream));
-            CUDA_TRY(cudaMemcpy2DAsync(ix->sc.q, stride * 4, d_queries, ix->dim * 4, ix->dim * 4, nq, cudaMemcpyDeviceToDevice, ix->stream));
-            qp = ix->sc.q;
-        }
-        ix->pending_out_keys = ix->sc.keys_local;  // K1's epilogue packs (distance bits, global id) keys
-        idb_status st = ix->enqueue_search(qp, nq, ef, k, ix->sc.ids, nullptr, nullptr);
-        ix->pending_out_keys = nullptr;
-        if (st != IDB_OK) return st;
-    }
-    NCCL_TRY(nccl().AllGather(ix->sc.keys_local, ix->sc.keys_all, per, ncclUint64, c->comm, ix->stream));
-    const int wpb = 4;
-    const size_t smem = (size_t)wpb * c->world * k * 8;
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)std::min<uint64_t>((nq + wpb - 1) / wpb, (uint64_t)ix->num_sms * 8);
-    merge_topk_kernel<<<grid, wpb * 32, smem, ix->stream>>>(ix->sc.keys_all, (uint32_t)c->world, nq, k, d_out_ids, d_out_dist, d_out_len);
-    CUDA_TRY(cudaGetLastError());
-    ix->last_launches += 2;  // all-gather + merge
-    return IDB_OK;
+    Lane& ln = ix->lanes[0];
+    std::lock_guard<std::mutex> lk(ln.mu);
+    ix->last_lane.store(0);
+    return sharded_search_locked(ix, c, ln, d_queries, nq, ef_search, k, d_out_ids, d_out_dist, d_out_len);
 }
 
 idb_status idb_sharded_search_batch_f32(idb_index* index, idb_comm* comm, const float* queries, uint64_t nq, uint32_t ef_search, uint32_t k,
                                         uint32_t* out_ids, float* out_dist, uint32_t* out_len) {
     if (!index || !comm) return fail(IDB_ERR_INVALID_ARG, "index/comm is null");
     Index* ix = reinterpret_cast<Index*>(index);
+    Comm* c = reinterpret_cast<Comm*>(comm);
     if (nq == 0) return IDB_OK;
     if (!queries || !out_ids || k == 0) return fail(IDB_ERR_INVALID_ARG, "bad argument");
-    float* dq = nullptr;
-    uint32_t *d_ids = nullptr, *d_len = nullptr;
-    float* d_dist = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(ix->mu);
-        CUDA_TRY(cudaSetDevice(ix->device));
-        CUDA_TRY(ensure_f32(ix->sc.q2, ix->sc.q2_cap, nq * ix->dim));
-        CUDA_TRY(ensure_u32(ix->sc.ids2, ix->sc.ids2_cap, nq * k));
-        CUDA_TRY(ensure_f32(ix->sc.dist, ix->sc.dist_cap, nq * k));
-        CUDA_TRY(ensure_u32(ix->sc.len, ix->sc.len_cap, nq));
-        dq = ix->sc.q2; d_ids = ix->sc.ids2; d_dist = ix->sc.dist; d_len = ix->sc.len;
-        CUDA_TRY(cudaMemcpyAsync(dq, queries, nq * ix->dim * 4, cudaMemcpyHostToDevice, ix->stream));
-    }
-    idb_status st = idb_sharded_search_batch_device(index, comm, dq, nq, ef_search, k, d_ids, d_dist, d_len);
+    Lane& ln = ix->lanes[0];
+    std::lock_guard<std::mutex> lk(ln.mu);  // held across staging, search and copy-back: the staging buffers belong to this call
+    ix->last_lane.store(0);
+    CUDA_TRY(cudaSetDevice(ix->device));
+    CUDA_TRY(ensure_f32(ln.q2, ln.q2_cap, nq * ix->dim));
+    CUDA_TRY(ensure_u32(ln.ids2, ln.ids2_cap, nq * k));
+    CUDA_TRY(ensure_f32(ln.dist, ln.dist_cap, nq * k));
+    CUDA_TRY(ensure_u32(ln.len, ln.len_cap, nq));
+    CUDA_TRY(cudaMemcpyAsync(ln.q2, queries, nq * ix->dim * 4, cudaMemcpyHostToDevice, ln.stream));
+    idb_status st = sharded_search_locked(ix, c, ln, ln.q2, nq, ef_search, k, ln.ids2, ln.dist, ln.len);
     if (st != IDB_OK) return st;
-    std::lock_guard<std::mutex> lk(ix->mu);
-    CUDA_TRY(cudaMemcpyAsync(out_ids, d_ids, nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
-    if (out_dist) CUDA_TRY(cudaMemcpyAsync(out_dist, d_dist, nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
-    if (out_len) CUDA_TRY(cudaMemcpyAsync(out_len, d_len, nq * 4, cudaMemcpyDeviceToHost, ix->stream));
-    uint32_t ctrl[16];
-    if (ix->sc.ctrl) CUDA_TRY(cudaMemcpyAsync(ctrl, ix->sc.ctrl, 64, cudaMemcpyDeviceToHost, ix->stream));
-    CUDA_TRY(cudaStreamSynchronize(ix->stream));
-    if (ix->sc.ctrl && ix->n && ctrl[12] != 0)
-        return fail(IDB_ERR_CAPACITY, "%u queries overflowed an internal per-query structure on this shard", ctrl[12]);
+    CUDA_TRY(cudaMemcpyAsync(out_ids, ln.ids2, nq * k * 4, cudaMemcpyDeviceToHost, ln.stream));
+    if (out_dist) CUDA_TRY(cudaMemcpyAsync(out_dist, ln.dist, nq * k * 4, cudaMemcpyDeviceToHost, ln.stream));
+    if (out_len) CUDA_TRY(cudaMemcpyAsync(out_len, ln.len, nq * 4, cudaMemcpyDeviceToHost, ln.stream));
+    uint32_t ctrl[16] = {0};
+    if (ln.ctrl && ln.last_nq) CUDA_TRY(cudaMemcpyAsync(ctrl, ln.ctrl, 64, cudaMemcpyDeviceToHost, ln.stream));
+    CUDA_TRY(cudaStreamSynchronize(ln.stream));
+    if (ctrl[12] != 0) return fail(IDB_ERR_CAPACITY, "%u queries overflowed an internal per-query structure on this shard", ctrl[12]);
     return IDB_OK;
 }
 

@@ -17,7 +17,8 @@ OK, ERR_INVALID_ARG, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_IO, ERR_FORMAT, ERR_CAPACI
 
 SYMBOLS = [
     "idb_params_default", "idb_build_f32", "idb_index_from_graph_f32", "idb_index_from_graph_bf16", "idb_search_batch_f32",
-    "idb_search_batch_device", "idb_last_search_counters", "idb_index_info", "idb_index_export_points",
+    "idb_search_batch_device", "idb_search_batch_device_lane", "idb_last_search_counters", "idb_last_search_failures",
+    "idb_index_num_lanes", "idb_index_lane_stream", "idb_device_set_persisting_l2", "idb_index_info", "idb_index_export_points",
     "idb_index_export_zero", "idb_index_export_upper", "idb_index_save", "idb_index_load", "idb_index_set_profiling", "idb_index_last_kernel_ms", "idb_debug_gather_bench", "idb_debug_gather_mix_bench",
     "idb_index_stream", "idb_index_sync", "idb_index_free",
     "idb_comm_unique_id", "idb_comm_create", "idb_comm_free", "idb_index_set_id_map", "idb_sharded_search_batch_f32",
@@ -67,7 +68,13 @@ def lib():
     L.idb_index_from_graph_bf16.argtypes = L.idb_index_from_graph_f32.argtypes
     L.idb_search_batch_f32.argtypes = [vp, f32p, C.c_uint64, C.c_uint32, C.c_uint32, u32p, f32p, u32p]
     L.idb_search_batch_device.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp]
+    L.idb_search_batch_device_lane.argtypes = [vp, C.c_uint32, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp]
     L.idb_last_search_counters.argtypes = [vp, C.c_uint64, u64p]
+    L.idb_last_search_failures.argtypes = [vp, C.c_uint32, u32p]
+    L.idb_index_num_lanes.restype = C.c_uint32
+    L.idb_index_lane_stream.argtypes = [vp, C.c_uint32]
+    L.idb_index_lane_stream.restype = vp
+    L.idb_device_set_persisting_l2.argtypes = [C.c_int32, C.c_int32]
     L.idb_index_info.argtypes = [vp, C.POINTER(Info)]
     L.idb_index_export_points.argtypes = [vp, f32p]
     L.idb_index_export_zero.argtypes = [vp, u32p]
@@ -99,7 +106,7 @@ def lib():
     L.idb_device_count.restype = C.c_int32
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("idb_index_stream", "idb_index_free", "idb_host_free", "idb_last_error", "idb_version", "idb_device_count",
+        if name not in ("idb_index_stream", "idb_index_lane_stream", "idb_index_num_lanes", "idb_index_free", "idb_host_free", "idb_last_error", "idb_version", "idb_device_count",
                         "idb_comm_free"):
             fn.restype = C.c_int
     _lib = L
@@ -195,10 +202,20 @@ class Index:
         check(lib().idb_index_info(self._h, C.byref(i)))
         return i
 
-    def search(self, queries, ef_search=0, k=None):
+    def _queries(self, queries):
+        """n x dim f32 matrix; narrower rows are zero-padded like the reference pads short points (py:363-375), wider ones rejected."""
         q = f32(queries)
         if q.ndim == 1:
             q = q[None, :]
+        dim = int(self.info().dim)
+        if q.shape[1] > dim:
+            raise ValueError(f"query has {q.shape[1]} elements, the index holds {dim}-d points (py:369-370: 'point array too long')")
+        if q.shape[1] < dim:
+            q = np.ascontiguousarray(np.pad(q, ((0, 0), (0, dim - q.shape[1]))))
+        return q
+
+    def search(self, queries, ef_search=0, k=None):
+        q = self._queries(queries)
         nq = q.shape[0]
         if k is None:
             k = ef_search or self.info().ef_search
@@ -209,8 +226,17 @@ class Index:
                                          ptr(dist, C.c_float), ptr(lens, C.c_uint32)))
         return ids, dist, lens
 
-    def search_device(self, d_queries, nq, ef_search, k, d_ids, d_dist, d_len):
-        check(lib().idb_search_batch_device(self._h, d_queries, nq, ef_search, k, d_ids, d_dist, d_len))
+    def search_device(self, d_queries, nq, ef_search, k, d_ids, d_dist, d_len, lane=0):
+        """Asynchronous: enqueues on submission lane `lane` (own stream; lanes overlap on the device)."""
+        check(lib().idb_search_batch_device_lane(self._h, lane, d_queries, nq, ef_search, k, d_ids, d_dist, d_len))
+
+    def lane_stream(self, lane):
+        return lib().idb_index_lane_stream(self._h, lane)
+
+    def last_failures(self, lane=0):
+        out = C.c_uint32()
+        check(lib().idb_last_search_failures(self._h, lane, C.byref(out)))
+        return int(out.value)
 
     def set_id_map(self, global_ids):
         """global_ids[pid] = caller's id of the row that became PointId pid; None clears the map."""
@@ -223,7 +249,7 @@ class Index:
         check(lib().idb_index_set_id_map(self._h, ptr(g, C.c_uint32)))
 
     def sharded_search(self, comm, queries, ef_search=0, k=10):
-        q = f32(queries)
+        q = self._queries(queries)
         nq = q.shape[0]
         ids = np.empty((nq, k), dtype=np.uint32)
         dist = np.empty((nq, k), dtype=np.float32)

@@ -139,7 +139,45 @@ float l2_sqrt_sequential(const float* a, const float* b, uint32_t dim) {
     return std::sqrt(s);
 }
 
-enum Metric : int { METRIC_L2SQ_CANONICAL = 0, METRIC_L2_SQRT_SEQ = 1 };
+// The reference's OWN summation order for its only f32-vector Point, FloatArray::distance (py:378-421): 8 AVX2 lanes, one FMA chain
+// per lane over chunks_exact(8); upper half + lower half; the last 4 elements FMA'd into the 4 sums; then (s0+s2)+(s1+s3).
+// The reference fixes DIMENSIONS = 300 (py:16) and asserts len % 8 == 4 (py:388); restated here for any dim with dim % 8 == 4.
+// Used only to MEASURE how often results differ from the product's canonical order (tests/, scripts/summation_order_gap.py).
+#define ORC_REF_ORDER_BODY                                                                                   \
+    float acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};                                                                \
+    const uint32_t body = dim / 8 * 8; /* chunks_exact(8) */                                                 \
+    for (uint32_t i = 0; i < body; i += 8)                                                                   \
+        for (int l = 0; l < 8; ++l) {                                                                        \
+            const float d = a[i + l] - b[i + l];                                                             \
+            acc8[l] = __builtin_fmaf(d, d, acc8[l]); /* _mm256_fmadd_ps (py:397) */                          \
+        }                                                                                                    \
+    float acc4[4];                                                                                           \
+    for (int l = 0; l < 4; ++l) acc4[l] = acc8[4 + l] + acc8[l]; /* py:400-402 */                            \
+    for (int l = 0; l < 4; ++l) {                                /* py:404-407: the LAST four elements */    \
+        const float d = a[dim - 4 + l] - b[dim - 4 + l];                                                     \
+        acc4[l] = __builtin_fmaf(d, d, acc4[l]);                                                             \
+    }                                                                                                        \
+    const float s0 = acc4[0] + acc4[2], s1 = acc4[1] + acc4[3]; /* movehl + add (py:409-410) */              \
+    return s0 + s1;                                             /* shuffle + add_ss (py:411-413) */
+float l2sq_reference_order_generic(const float* a, const float* b, uint32_t dim) { ORC_REF_ORDER_BODY }
+#if defined(__x86_64__)
+__attribute__((target("avx2,fma"))) float l2sq_reference_order_fma(const float* a, const float* b, uint32_t dim) { ORC_REF_ORDER_BODY }
+#endif
+#undef ORC_REF_ORDER_BODY
+float l2sq_reference_avx2_order(const float* a, const float* b, uint32_t dim) {
+#if defined(__x86_64__)
+    static const bool have_fma = (__builtin_cpu_init(), __builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2"));
+    if (have_fma) return l2sq_reference_order_fma(a, b, dim);  // same IEEE results, hardware fma instead of libm's
+#endif
+    return l2sq_reference_order_generic(a, b, dim);
+}
+
+enum Metric : int { METRIC_L2SQ_CANONICAL = 0, METRIC_L2_SQRT_SEQ = 1, METRIC_L2SQ_REFERENCE_AVX2 = 2 };
+dist_fn metric_fn(int metric) {
+    if (metric == METRIC_L2_SQRT_SEQ) return l2_sqrt_sequential;
+    if (metric == METRIC_L2SQ_REFERENCE_AVX2) return l2sq_reference_avx2_order;
+    return g_l2sq;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Candidate ordering (types:228-234): derived lexicographic Ord on (OrderedFloat<f32>, PointId).
@@ -266,7 +304,7 @@ struct orc_index {
     Points pts() const {
         Points p;
         p.base = points; p.stride = stride; p.dim = dim;
-        p.fn = metric == METRIC_L2_SQRT_SEQ ? l2_sqrt_sequential : g_l2sq;
+        p.fn = metric_fn(metric);
         return p;
     }
     ~orc_index() { std::free(points); }
@@ -638,6 +676,7 @@ ORC_API void orc_params_default(orc_params* p) {
 ORC_API float orc_default_ml(uint32_t M) { return 1.0f / std::log((float)M); }
 
 ORC_API float orc_l2sq(const float* a, const float* b, uint32_t dim) { return g_l2sq(a, b, dim); }
+ORC_API float orc_l2sq_reference_order(const float* a, const float* b, uint32_t dim) { return l2sq_reference_avx2_order(a, b, dim); }
 ORC_API float orc_l2sq_scalar(const float* a, const float* b, uint32_t dim) { return l2sq_canonical_scalar(a, b, dim); }
 ORC_API int orc_simd_level() { return g_l2sq == l2sq_canonical_scalar ? 0 : 512; }
 
@@ -812,7 +851,7 @@ ORC_API int orc_search(const orc_index* ix, const float* queries, uint64_t nq, u
 // Exact k-NN by exhaustive scan with the index's metric; ties by lower id.  Ground truth for recall.
 ORC_API int orc_bruteforce(const float* points, uint64_t n, uint32_t dim, const float* queries, uint64_t nq, uint32_t k,
                            uint32_t* out_ids, float* out_dist, int32_t metric, int32_t threads) {
-    dist_fn fn = metric == METRIC_L2_SQRT_SEQ ? l2_sqrt_sequential : g_l2sq;
+    dist_fn fn = metric_fn(metric);
     const size_t stride = ((size_t)dim + 3) / 4 * 4;
     float* prow = alloc_rows(n ? n : 1, stride);
     for (uint64_t r = 0; r < n; ++r) std::memcpy(prow + r * stride, points + r * dim, dim * sizeof(float));

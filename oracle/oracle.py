@@ -52,6 +52,8 @@ def lib():
     L.orc_l2sq.argtypes = [f32p, f32p, C.c_uint32]
     L.orc_l2sq_scalar.restype = C.c_float
     L.orc_l2sq_scalar.argtypes = [f32p, f32p, C.c_uint32]
+    L.orc_l2sq_reference_order.restype = C.c_float
+    L.orc_l2sq_reference_order.argtypes = [f32p, f32p, C.c_uint32]
     L.orc_simd_level.restype = C.c_int
     L.orc_layer_schedule.restype = C.c_uint32
     L.orc_layer_schedule.argtypes = [C.c_uint64, C.c_uint32, C.c_float, u64p, C.c_uint32]
@@ -102,6 +104,16 @@ def l2sq(a, b, scalar=False):
     a, b = _f32(a), _f32(b)
     fn = lib().orc_l2sq_scalar if scalar else lib().orc_l2sq
     return np.float32(fn(_p(a, C.c_float), _p(b, C.c_float), a.shape[0]))
+
+
+METRIC_CANONICAL, METRIC_SQRT_SEQ, METRIC_REFERENCE_AVX2 = 0, 1, 2
+
+
+def l2sq_reference_order(a, b):
+    """FloatArray::distance in the reference's own AVX2 summation order (py:378-421); needs dim % 8 == 4 (the reference: 300)."""
+    a, b = _f32(a), _f32(b)
+    assert a.shape[0] % 8 == 4 and a.shape == b.shape
+    return np.float32(lib().orc_l2sq_reference_order(_p(a, C.c_float), _p(b, C.c_float), a.shape[0]))
 
 
 def layer_schedule(n, M=32, ml=None):

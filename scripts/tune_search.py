@@ -22,7 +22,7 @@ ap.add_argument("--data", default="sift")
 ap.add_argument("--graph", default="gpu")
 ap.add_argument("--batch", type=int, default=10000)
 ap.add_argument("--steps", type=int, default=5)
-ap.add_argument("--configs", default="IDB_OPT=0;IDB_VIS_BUCKETS=0;IDB_VIS_BUCKETS=0,IDB_VIS_BITMAP=0;IDB_OPT=16")
+ap.add_argument("--configs", default="IDB_OPT=0;IDB_VIS_TIER=1;IDB_VIS_TIER=0;IDB_B16_BYTES=16384;IDB_B16_BYTES=32768;IDB_L2_PERSIST=0")
 args = ap.parse_args()
 args.no_cache = False
 
@@ -47,7 +47,7 @@ d_dist = torch.empty((args.batch, k), dtype=torch.float32, device="cuda")
 d_len = torch.empty((args.batch,), dtype=torch.int32, device="cuda")
 ref_ids = None
 results = []
-KNOBS = ["IDB_OPT", "IDB_VIS_MULT", "IDB_CTAS_PER_SM", "IDB_VARIANT", "IDB_VIS_BITMAP", "IDB_VIS_BUCKETS"]
+KNOBS = ["IDB_OPT", "IDB_VIS_MULT", "IDB_CTAS_PER_SM", "IDB_VARIANT", "IDB_VIS_TIER", "IDB_B16_BYTES", "IDB_L2_PERSIST"]
 for cfg in args.configs.split(";"):
     for kname in KNOBS:
         os.environ.pop(kname, None)

@@ -78,7 +78,7 @@ def test_search_parity_10k_x32_config0(abi, oracle):
 
 
 def test_search_parity_pid_space_beyond_16_bits(abi, oracle):
-    """n > 65535: the b16 visited tables (IDB_VIS_MODE 1/2) split a PointId into (quotient, 16-bit remainder)."""
+    """n > 65535: the b16 visited tables (the b16 flavour) split a PointId into (quotient, 16-bit remainder)."""
     pts = datagen.uniform(150_000, 8, 3)
     ix, _ = oracle.build(pts, seed=5, threads=8)
     _check(abi, oracle, ix.export(), ix, datagen.uniform(2000, 8, 4), 100, k=10)
@@ -220,12 +220,12 @@ def test_visited_overflow_goes_through_the_retry_pass(abi, oracle, monkeypatch):
     assert (gpu.last_counters(len(q)) == want[3]).all()
 
 
-FLAVOURS = {"buckets": {}, "bitmap": {"IDB_VIS_BUCKETS": "0"}, "hash": {"IDB_VIS_BUCKETS": "0", "IDB_VIS_BITMAP": "0"}}
+FLAVOURS = {"b16": {}, "bitmap": {"IDB_VIS_TIER": "1"}, "hash": {"IDB_VIS_TIER": "0"}}
 
 
 @pytest.mark.parametrize("flavour", sorted(FLAVOURS))
 def test_search_parity_every_visited_flavour(abi, oracle, monkeypatch, flavour):
-    """The wide-layer visited set has three exact flavours (bucket set in L2 / bitmap / hash set); all must give the oracle's answer."""
+    """The wide-layer visited set has three exact flavours (16-bit-tag bucket set in L2 / bitmap / hash set); all must give the oracle's answer."""
     for k_, v_ in FLAVOURS[flavour].items():
         monkeypatch.setenv(k_, v_)
     for n, dim, M, ef, seed in [(5000, 128, 32, 100, 1), (3000, 16, 64, 200, 2), (4000, 300, 24, 100, 3)]:
@@ -245,7 +245,7 @@ def test_bucket_set_overflow_goes_through_the_retry_pass(abi, oracle, monkeypatc
     q = datagen.uniform(300, 16, 14)
     want = ix.search(q, ef_search=100, k=10, counters=True)
     assert want[3][:, 3].max() > 1024
-    monkeypatch.setenv("IDB_BUCKET_SLOTS", "1024")
+    monkeypatch.setenv("IDB_B16_BYTES", "2048")  # 64 buckets x 16 slots, handed to the retry pass beyond 704 ids
     gpu = abi.Index.from_graph(g.points, g.zero, g.upper, g.M)
     got = gpu.search(q, ef_search=100, k=10)
     assert (got[0] == want[0]).all() and got[1].tobytes() == want[1].tobytes() and (got[2] == want[2]).all()
@@ -254,7 +254,8 @@ def test_bucket_set_overflow_goes_through_the_retry_pass(abi, oracle, monkeypatc
 
 @pytest.mark.parametrize("flavour", sorted(FLAVOURS))
 def test_rows_with_repeated_ids(abi, oracle, monkeypatch, flavour):
-    """An adopted graph may list a PointId twice in one row (the reference's Visited then skips the second, types.rs:32-40)."""
+    """An adopted graph may list a PointId twice in one row (the reference's Visited then skips the second, types.rs:32-40).
+    The upload-time check notices and keeps such an index off the b16 flavour (which assumes distinct ids per row)."""
     for k_, v_ in FLAVOURS[flavour].items():
         monkeypatch.setenv(k_, v_)
     pts = datagen.uniform(4000, 24, 5)
