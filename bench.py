@@ -3,15 +3,26 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, through the C ABI)
   python bench.py --impl reference [...]                         reference arm: the CPU path on the box's host cores
+  python bench.py --mode build|sharded|headline [...]            one leg only (default --mode auto, below)
 
-A "step" = one pass of the hot path (Hnsw::search, lib.rs:352-383) over one batch of `--batch` synthetic queries.
-Workload at N=1 = BASELINE.json configs[1]: 1M x 128 f32 "SIFT-shaped" synthetic points, M=32, ef_construction=100,
-ef_search=100 (raised only if recall@10 < 0.95), batch = 10k queries.  N>1: every rank holds a replica of the index
-and searches its own batch (queries are independent objects -> no data-path collective; "scaling": "weak").
-`value` = queries/s with queries + outputs resident in HBM; `e2e` = the same through idb_search_batch_f32 with pinned
-HOST buffers (H2D + D2H inside the timed region).  The index (512 MB points + 308 MB adjacency) is far larger than the
-126 MB L2 and every step uses a different query batch, so no L2 flush is needed between iterations.
-torch is used only as plumbing: device buffers, CUDA events, torch.distributed, and the brute-force recall reference.
+A "step" = one pass of the hot path (Hnsw::search, lib.rs:352-383) over one batch of synthetic queries.
+
+--gpus 1 (auto): BASELINE.json configs[1] — 1M x 128 f32 "SIFT-shaped" synthetic points, M=32, ef_construction=100, ef_search=100
+  (raised only if recall@10 < 0.95), batch = 10k queries.  `value` = queries/s with queries + outputs resident in HBM (batches
+  issued alternately on two submission lanes, so consecutive launches overlap at the batch boundary); `e2e` = the same through
+  idb_search_batch_f32 with pinned HOST buffers (H2D + D2H inside the timed region, two caller threads).  The line also carries
+  `sharded` (BASELINE configs[4] on ONE GPU: 10M x 128 in 8 sub-indexes by contiguous input range, batch 100k — the denominator of
+  the 1 -> 8 GPU figure north_star asks for) and `uniform` (the same headline kernel on uniform-random data).
+--gpus N > 1 (auto): BASELINE.json configs[4] — the same 8 sub-indexes spread over the N GPUs (8/N each), every query searched on
+  every sub-index, per-rank pre-merge, ONE ncclAllGather of the per-rank top-k, merge kernel (idb_sharded_search_batch_*_multi).
+  `value` = queries/s of the whole job ("scaling": "strong"); `replicas` carries the configs[1] replica figure (queries sharded
+  over N copies of the 1M index, no collective) as a secondary field.
+--impl reference: the reference algorithm's CPU path (oracle/ restatement; the Rust crate cannot be built here) with all host
+  threads, on the same config: N=1 -> configs[1]; N>1 -> configs[4] (rank 0 only; the other ranks exit).  It never loads the CUDA
+  library: the graph both arms search is built in an untimed setup step by lib/idb_build_graph (a C++ program over the C ABI).
+
+The indexes (>= 512 MB points + 308 MB adjacency) are far larger than the 126 MB L2 and every step uses a different query batch,
+so no L2 flush is needed between iterations.  torch is plumbing only: device buffers, CUDA events, torch.distributed, brute force.
 """
 import argparse
 import ctypes as C
@@ -31,15 +42,9 @@ sys.path.insert(0, os.path.join(ROOT, "instant-distance_b200", "python"))
 
 from tests import datagen  # noqa: E402  (seeded synthetic data shared with the tests)
 
-
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE K1 launch at the headline config, from the committed ncu --set full
-    capture of the current kernel (profiles/k1_ncu_traffic.json names the capture it was read from)."""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "k1_ncu_traffic.json")))
-        return float(d["dram_bytes_per_launch"]), d["source"]
-    except Exception:  # noqa: BLE001
-        return None, None
+TOOL = os.path.join(ROOT, "instant-distance_b200", "lib", "idb_build_graph")
+K = 10  # results per query (recall@10)
+N_SUB = 8  # sub-indexes of the sharded config
 
 
 def log(*a):
@@ -69,6 +74,16 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE K1 launch at the headline config, from the committed ncu --set full
+    capture of the current kernel (profiles/k1_ncu_traffic.json names the capture it was read from)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "k1_ncu_traffic.json")))
+        return float(d["dram_bytes_per_launch"]), d["source"]
+    except Exception:  # noqa: BLE001
+        return None, None
 
 
 class ClockSampler:
@@ -126,19 +141,11 @@ class ClockSampler:
                 "samples": len(rows), "power_w_max": max(r[3] for r in rows)}
 
 
-def make_workload(args):
-    gen = datagen.sift_shaped if args.data == "sift" else datagen.uniform
-    t = time.time()
-    pts = gen(args.n, args.dim, 1)
-    log(f"generated {args.n} x {args.dim} {args.data} points in {time.time() - t:.1f}s")
-    return pts, gen
-
-
-def graph_cache_path(args):
-    key = f"{args.n}-{args.dim}-{args.data}-{args.M}-{args.efc}-{args.graph}-{args.seed}-v2"
-    d = os.environ.get("IDB_CACHE", os.path.join(ROOT, "gpurun_cache"))
-    os.makedirs(d, exist_ok=True)
-    return os.path.join(d, "graph_" + hashlib.sha1(key.encode()).hexdigest()[:16] + ".npz")
+# ---------------------------------------------------------------------------------------------------------------------
+# workloads and graphs (setup; never timed)
+# ---------------------------------------------------------------------------------------------------------------------
+def generator(data):
+    return datagen.sift_shaped if data == "sift" else datagen.uniform
 
 
 def permute_points(pts, ids):
@@ -147,45 +154,96 @@ def permute_points(pts, ids):
     return p
 
 
-def obtain_graph(args, pts, device):
-    """Returns (points in PointId order, zero, upper list, how).  Setup, never timed.
-    The graph (not the points, which are regenerated from the seed) is cached under gpurun_cache/ (git-ignored)."""
-    from instant_distance_b200 import _abi
+def cache_dir():
+    d = os.environ.get("IDB_CACHE", os.path.join(ROOT, "gpurun_cache"))
+    os.makedirs(d, exist_ok=True)
+    return d
 
-    cp = graph_cache_path(args)
-    if os.path.exists(cp) and not args.no_cache:
+
+def graph_cache_path(n, dim, data, data_seed, M, efc, seed):
+    key = f"{n}-{dim}-{data}-{data_seed}-{M}-{efc}-{seed}-v3"
+    return os.path.join(cache_dir(), "graph_" + hashlib.sha1(key.encode()).hexdigest()[:16] + ".npz")
+
+
+def build_graph_with_tool(pts, M, efc, ef, seed, device):
+    """Graph of `pts` by the GPU Builder::build, through lib/idb_build_graph (a separate C++ process over the C ABI).
+    Returns (ids, zero, upper list, build seconds)."""
+    n, dim = pts.shape
+    base = os.path.join(cache_dir(), f"tool_{os.getpid()}")
+    raw = base + ".points.f32"
+    np.ascontiguousarray(pts, dtype=np.float32).tofile(raw)
+    try:
+        r = subprocess.run([TOOL, raw, str(n), str(dim), str(M), str(efc), str(ef), str(seed), str(device), base],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"idb_build_graph failed: {r.stderr.strip()[-400:]}")
+        meta = open(base + ".meta").read().split()
+        n_layers = int(meta[3])
+        layer_n = [int(x) for x in meta[4:4 + n_layers]]
+        ids = np.fromfile(base + ".ids.u32", dtype=np.uint32)
+        zero = np.fromfile(base + ".zero.u32", dtype=np.uint32).reshape(n, 2 * M)
+        upper = [np.fromfile(f"{base}.upper{l}.u32", dtype=np.uint32).reshape(layer_n[l], M) for l in range(1, n_layers)]
+        return ids, zero, upper, float(meta[4 + n_layers])
+    finally:
+        for f in os.listdir(cache_dir()):
+            if f.startswith(os.path.basename(base) + "."):
+                os.remove(os.path.join(cache_dir(), f))
+
+
+def obtain_graph(pts, n, dim, data, data_seed, M, efc, ef, seed, device, use_abi, no_cache=False):
+    """(points in PointId order, zero, upper, ids).  The graph is the GPU Builder::build's (deterministic in the seed): built
+    in-process when the caller is the CUDA arm (use_abi), else by the C++ tool; cached under gpurun_cache/ (git-ignored)."""
+    cp = graph_cache_path(n, dim, data, data_seed, M, efc, seed)
+    if os.path.exists(cp) and not no_cache:
         z = np.load(cp)
-        upper = [z[f"u{i}"] for i in range(int(z["n_upper"]))]
-        log(f"graph loaded from cache {cp}")
-        return permute_points(pts, z["ids"]), z["zero"], upper, str(z["how"]) + " [cached]"
-    how = None
-    if args.graph == "gpu":
-        try:
-            t = time.time()
-            ix, ids = _abi.Index.build(pts, M=args.M, ef_construction=args.efc, ef_search=args.ef, seed=args.seed, device=device)
-            _, zero, upper = ix.export_graph()
-            ix.close()
-            how = f"GPU Builder::build ({time.time() - t:.1f}s)"
-        except _abi.IdbError as e:
-            if e.status != _abi.ERR_UNSUPPORTED:
-                raise
-            log("GPU build unavailable:", e)
-    if how is None:
-        from oracle import oracle as O  # setup only: the reference algorithm builds the graph the GPU then searches
+        log(f"graph loaded from cache {os.path.basename(cp)}")
+        return permute_points(pts, z["ids"]), z["zero"], [z[f"u{i}"] for i in range(int(z["n_upper"]))], z["ids"]
+    t = time.time()
+    if use_abi:
+        from instant_distance_b200 import _abi
 
-        T = host_threads()
-        t = time.time()
-        ix, ids = O.build(pts, M=args.M, ef_construction=args.efc, ef_search=args.ef, seed=args.seed, threads=T)
+        ix, ids = _abi.Index.build(pts, M=M, ef_construction=efc, ef_search=ef, seed=seed, device=device)
+        _, zero, upper = ix.export_graph()
+        ix.close()
+    elif os.path.exists(TOOL):
+        try:
+            ids, zero, upper, _ = build_graph_with_tool(pts, M, efc, ef, seed, device)
+        except Exception as e:  # noqa: BLE001  (no GPU on this box: the reference algorithm builds it on the CPU)
+            log("GPU graph tool unavailable:", e)
+            ids = None
+    else:
+        ids = None
+    if ids is None:
+        from oracle import oracle as O
+
+        ix, ids = O.build(pts, M=M, ef_construction=efc, ef_search=ef, seed=seed, threads=host_threads())
         g = ix.export()
         zero, upper = g.zero, g.upper
-        how = f"oracle (reference algorithm) threaded build, {T} threads ({time.time() - t:.1f}s)"
-    log("graph:", how)
-    if not args.no_cache:
+        log("graph built by the oracle (CPU) — NOT the GPU build's graph")
+    log(f"graph built in {time.time() - t:.1f}s (setup, untimed)")
+    if not no_cache:
         try:
-            np.savez(cp, ids=ids, zero=zero, n_upper=len(upper), how=how, **{f"u{i}": u for i, u in enumerate(upper)})
+            np.savez(cp, ids=ids, zero=zero, n_upper=len(upper), **{f"u{i}": u for i, u in enumerate(upper)})
         except Exception as e:  # cache is best effort
             log("cache write failed:", e)
-    return permute_points(pts, ids), zero, upper, how
+    return permute_points(pts, ids), zero, upper, ids
+
+
+GRAPH_NOTE = "GPU Builder::build of this library (deterministic in the seed; untimed setup), searched by both arms"
+
+
+def search_config(a, world, mode):
+    par = "1 GPU" if world == 1 else f"replica x{world}, queries sharded, no collective"
+    return {"workload": f"{a.n} x {a.dim} f32 {a.data}-shaped synthetic, M={a.M}, ef_construction={a.efc}, ef_search={a.ef}, "
+                        f"batch={a.batch} queries/step, k={K}",
+            "graph": GRAPH_NOTE, "l2": "index >> 126 MB L2 and a fresh query batch per step (no flush needed)", "parallelism": par}
+
+
+def sharded_config(a, world):
+    return {"workload": f"{N_SUB} x {a.shard_n} = {N_SUB * a.shard_n} x {a.dim} f32 sift-shaped synthetic in {N_SUB} sub-indexes by contiguous "
+                        f"input range, M={a.M}, ef_construction={a.efc}, ef_search={a.ef}, batch={a.shard_batch} queries/step, k={K}",
+            "graph": GRAPH_NOTE, "l2": "every sub-index >> 126 MB L2 and a fresh query batch per step (no flush needed)",
+            "parallelism": f"{N_SUB} sub-indexes over {world} GPU(s) ({N_SUB // world} per GPU), per-rank pre-merge + ONE ncclAllGather + merge"}
 
 
 def brute_force_topk_torch(points_dev, queries, k):
@@ -193,12 +251,14 @@ def brute_force_topk_torch(points_dev, queries, k):
 
     q = torch.from_numpy(queries).to(points_dev.device)
     pn = (points_dev * points_dev).sum(1)
-    out = []
+    ids, ds = [], []
     for s in range(0, q.shape[0], 256):
         qq = q[s:s + 256]
         d = pn[None, :] - 2.0 * (qq @ points_dev.T) + (qq * qq).sum(1)[:, None]
-        out.append(torch.topk(d, k, dim=1, largest=False).indices.cpu())
-    return torch.cat(out).numpy()
+        t = torch.topk(d, k, dim=1, largest=False)
+        ids.append(t.indices.cpu())
+        ds.append(t.values.cpu())
+    return torch.cat(ids).numpy(), torch.cat(ds).numpy()
 
 
 def recall_at_k(ids, truth, k=10):
@@ -208,59 +268,480 @@ def recall_at_k(ids, truth, k=10):
     return hit / (k * len(ids))
 
 
-def algorithmic_bytes(counters, dim, M, k):
+def algorithmic_bytes(counters, dim, M, k, elem=4):
     """B(q) = vec + sum_layers[n_expand_l * row_bytes_l + n_dist_l * vec] + k*8."""
-    vec = dim * 4
+    vec = dim * elem
     c = counters.astype(np.float64)
-    per_q = vec + c[:, 0] * (M * 4) + c[:, 1] * vec + c[:, 2] * (2 * M * 4) + c[:, 3] * vec + k * 8
+    per_q = dim * 4 + c[:, 0] * (M * 4) + c[:, 1] * vec + c[:, 2] * (2 * M * 4) + c[:, 3] * vec + k * 8
     return per_q
 
 
-def run_reference(args, rank, world):
-    """Reference arm: the CPU path (oracle restatement; the Rust reference cannot be built here) on the host cores."""
+def cpu_qps(search_fn, batches, warm, timed):
+    """The ONE CPU-baseline protocol (in-arm leg and reference arm): `warm` untimed passes, then `timed` passes."""
+    for b in batches[:warm]:
+        search_fn(b)
+    t0 = time.perf_counter()
+    for b in batches[warm:warm + timed]:
+        search_fn(b)
+    dt = time.perf_counter() - t0
+    return sum(len(b) for b in batches[warm:warm + timed]) / dt, dt
+
+
+def pinned(nbytes, dtype, shape):
+    from instant_distance_b200 import _abi
+
+    p = C.c_void_p()
+    _abi.check(_abi.lib().idb_host_alloc(nbytes, C.byref(p)))
+    buf = (C.c_char * nbytes).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def reduce_max(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# leg: one index per rank, queries sharded over ranks (BASELINE configs[1] at N = 1)
+# ---------------------------------------------------------------------------------------------------------------------
+def leg_search(a, rank, local_rank, world, full=True):
+    import torch
+
+    from instant_distance_b200 import _abi
+
+    gen = generator(a.data)
+    pts = gen(a.n, a.dim, 1)
+    p, zero, upper, _ = obtain_graph(pts, a.n, a.dim, a.data, 1, a.M, a.efc, a.ef, a.seed, local_rank, use_abi=True,
+                                     no_cache=a.no_cache or world > 1)
+    del pts
+    ix = _abi.Index.from_graph(p, zero, upper, a.M, a.ef, device=local_rank)
+    ix.set_profiling(True)
+
+    # ---- recall gate: raise ef_search until recall@10 >= 0.95 on a sample --------------------------------------
+    pdev = torch.from_numpy(p).cuda()
+    rq = gen(a.recall_sample, a.dim, 999)
+    truth, _ = brute_force_topk_torch(pdev, rq, K)
+    del pdev
+    torch.cuda.empty_cache()
+    ef, recall = a.ef, 0.0
+    for cand in [a.ef, 128, 160, 200, 256, 320, 400, 512, 768, 1024]:
+        if cand < a.ef:
+            continue
+        ids, _, _ = ix.search(rq, ef_search=cand, k=K)
+        ef, recall = cand, recall_at_k(ids, truth)
+        log(f"[{a.data}] recall@10 = {recall:.4f} at ef_search = {cand}")
+        if recall >= 0.95 or not full:  # the secondary (uniform-data) line stays at the config's ef_search
+            break
+    else:
+        log("WARNING: recall@10 < 0.95 even at ef_search = 1024")
+
+    # ---- device-resident arm ("value"): batches alternate over two submission lanes ----------------------------------
+    total = a.warmup + a.steps
+    nq = a.batch
+    host_q = [gen(nq, a.dim, 5000 + 977 * rank + s) for s in range(total)]
+    dq = [torch.from_numpy(q).cuda() for q in host_q]
+    lanes = 2
+    d_ids = [torch.empty((nq, K), dtype=torch.int32, device="cuda") for _ in range(lanes)]
+    d_dist = [torch.empty((nq, K), dtype=torch.float32, device="cuda") for _ in range(lanes)]
+    d_len = [torch.empty((nq,), dtype=torch.int32, device="cuda") for _ in range(lanes)]
+    streams = [torch.cuda.ExternalStream(ix.lane_stream(l), device=local_rank) for l in range(lanes)]
+    torch.cuda.synchronize()
+
+    def step(s, lane):
+        ix.search_device(dq[s].data_ptr(), nq, ef, K, d_ids[lane].data_ptr(), d_dist[lane].data_ptr(), d_len[lane].data_ptr(), lane=lane)
+
+    for s in range(a.warmup):
+        step(s, s % lanes)
+    ix.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    barrier(world)
+    torch.cuda.synchronize()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(lanes)]
+    t_wall0 = time.time()
+    ev0.record(streams[0])
+    streams[1].wait_event(ev0)
+    launches = 0
+    for s in range(a.warmup, total):
+        step(s, s % lanes)
+        launches += 2  # K1 search_kernel + its (normally idle) overflow-retry launch; the control-block memset is not a kernel
+    for l in range(lanes):
+        ends[l].record(streams[l])
+    for l in range(lanes):
+        ends[l].synchronize()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    barrier(world)
+    dev_ms = reduce_max(max(ev0.elapsed_time(e) for e in ends), world)
+    clocks = sampler.summarize(sampler.window(t_wall0, t_wall1))
+    sampler.stop()
+    qps = world * nq * a.steps / (dev_ms / 1e3)
+
+    # isolated launches (one lane, event-bracketed per launch) + algorithmic bytes, on a second pass
+    iso_ms, alg_bytes = [], []
+    for s in range(a.warmup, total):
+        step(s, 0)
+        ms, _ = ix.last_kernel_ms()
+        iso_ms.append(ms)
+        alg_bytes.append(float(algorithmic_bytes(ix.last_counters(nq), a.dim, a.M, K).sum()))
+    assert ix.last_failures(0) == 0
+    alg = float(np.mean(alg_bytes))
+    peak, peak_src = measured_peaks()
+    k_ms = dev_ms / a.steps
+    res = {
+        "value": qps, "ms_per_step": dev_ms / a.steps, "recall_at_10": recall, "ef_search": ef, "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": alg / (k_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg / (k_ms / 1e3) / 1e9 / peak, "traffic": None, "kernel": "search_kernel (K1 search_layer)",
+                     "kernel_ms": k_ms, "kernel_ms_note": "timed region / launches, two launches in flight (successive launches overlap at the batch boundary)",
+                     "kernel_ms_isolated": float(np.mean(iso_ms)), "frac_isolated": alg / (float(np.mean(iso_ms)) / 1e3) / 1e9 / peak,
+                     "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+    }
+    if a.n == 1_000_000 and a.dim == 128 and a.batch == 10_000 and a.data == "sift":
+        res["roofline"]["traffic"], res["roofline"]["traffic_source"] = ncu_traffic()
+    if not full:
+        ix.close()
+        return res
+
+    # ---- e2e arm: public host API, pinned host buffers, H2D + D2H inside the timed region, two caller threads --------------
+    L = _abi.lib()
+    hqs = []
+    for s_ in range(total):
+        h = pinned(nq * a.dim * 4, np.float32, (nq, a.dim))
+        h[...] = host_q[s_]
+        hqs.append(h)
+    callers = 2
+    hid = [pinned(nq * K * 4, np.uint32, (nq, K)) for _ in range(callers)]
+    hds = [pinned(nq * K * 4, np.float32, (nq, K)) for _ in range(callers)]
+    hln = [pinned(nq * 4, np.uint32, (nq,)) for _ in range(callers)]
+    last_ids = {}
+
+    def e2e_step(s, t):
+        _abi.check(L.idb_search_batch_f32(ix._h, _abi.ptr(hqs[s], C.c_float), nq, ef, K, _abi.ptr(hid[t], C.c_uint32),
+                                          _abi.ptr(hds[t], C.c_float), _abi.ptr(hln[t], C.c_uint32)))
+
+    def e2e_run(lo, hi):
+        def work(t):
+            for s in range(lo + t, hi, callers):
+                e2e_step(s, t)
+                if s == total - 1:
+                    last_ids["ids"], last_ids["dist"], last_ids["len"] = hid[t].copy(), hds[t].copy(), hln[t].copy()
+        th = [threading.Thread(target=work, args=(t,)) for t in range(callers)]
+        [x.start() for x in th]
+        [x.join() for x in th]
+
+    e2e_run(0, a.warmup)
+    barrier(world)
+    t0 = time.perf_counter()
+    e2e_run(a.warmup, total)
+    e2e_s = reduce_max(time.perf_counter() - t0, world)
+    res["e2e"] = {"value": world * nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * a.dim * 4,
+                  "d2h_bytes_per_step": nq * K * 8 + nq * 4, "callers": callers}
+
+    # ---- CPU baseline (rank 0, N=1 leg only) + parity against it: ids, distances, lengths AND traversal counters -------------
+    res["cpu_baseline"] = None
+    if rank == 0 and world == 1 and not a.skip_cpu_baseline:
+        from oracle import oracle as O
+
+        T = host_threads()
+        ox = O.from_graph(O.Graph(p, zero, upper, a.M, ef))
+        sample = min(nq, a.ref_sample)
+        o_ids, o_dist, o_len, o_cnt = ox.search(host_q[total - 1][:sample], ef_search=ef, k=K, threads=T, counters=True)
+        ix.search(host_q[total - 1][:sample], ef_search=ef, k=K)
+        g_cnt = ix.last_counters(sample)
+        same = bool((o_ids == last_ids["ids"][:sample]).all() and o_dist.tobytes() == last_ids["dist"][:sample].tobytes()
+                    and (o_len == last_ids["len"][:sample]).all() and (o_cnt == g_cnt).all())
+        if not same:
+            log("PARITY FAILURE: GPU results differ from the oracle on the same graph")
+        batches = [q[:sample] for q in host_q[:8]]
+        v, dt = cpu_qps(lambda b: ox.search(b, ef_search=ef, k=K, threads=T), batches, 3, len(batches) - 3)
+        res["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": T, "kind": "port",
+                               "sample": f"{len(batches) - 3} passes of {sample} queries after 3 warm passes ({dt:.1f} s), same graph, ef_search={ef}, "
+                                         f"{T} threads (one Search per thread); GPU ids/distances/lengths/counters identical to the oracle's: {same}"}
+        res["parity_ok"] = same
+    ix.close()
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# leg: BASELINE configs[4] — 8 sub-indexes by contiguous input range over `world` GPUs, one all-gather per batch
+# ---------------------------------------------------------------------------------------------------------------------
+def shard_points(a, s):
+    return datagen.sift_shaped(a.shard_n, a.dim, 1000 + s)
+
+
+def leg_sharded(a, rank, local_rank, world, full=True):
+    import torch
+    import torch.distributed as dist
+
+    from instant_distance_b200 import _abi
+    from instant_distance_b200 import sharded as SH
+
+    assert N_SUB % world == 0, "the sharded config needs 1, 2, 4 or 8 GPUs"
+    per = N_SUB // world
+    mine = list(range(rank * per, (rank + 1) * per))
+    gen = datagen.sift_shaped
+    shards, gmaps, t_build = [], [], 0.0
+    rq = gen(a.recall_sample, a.dim, 999)
+    truth_local = []
+    for s in mine:
+        pts = shard_points(a, s)
+        t = time.time()
+        ix, ids = _abi.Index.build(pts, M=a.M, ef_construction=a.efc, ef_search=a.ef, seed=a.seed + s, device=local_rank)
+        t_build += time.time() - t
+        gmaps.append(SH.global_id_map(ids, s * a.shard_n))
+        ix.set_id_map(gmaps[-1])
+        shards.append(ix)
+        pdev = torch.from_numpy(pts).cuda()  # exact top-10 of the sample queries on this sub-index (for recall)
+        ti, td = brute_force_topk_torch(pdev, rq, K)
+        truth_local.append((td, ti.astype(np.int64) + s * a.shard_n))
+        del pdev, pts
+        torch.cuda.empty_cache()
+    log(f"rank {rank}: built sub-indexes {mine} in {t_build:.1f}s (Builder::build on the GPU, setup)")
+    uid = _abi.comm_unique_id() if rank == 0 else None
+    if world > 1:
+        box = [uid]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+    comm = _abi.Comm(uid, rank, world, local_rank)
+    shards[0].set_profiling(True)
+
+    total = a.warmup + a.steps
+    nq = a.shard_batch
+    dq_pool = [torch.from_numpy(gen(nq, a.dim, 7000 + s)).cuda() for s in range(min(total, 6))]  # identical on every rank
+    d_ids = torch.empty((nq, K), dtype=torch.int32, device="cuda")
+    d_dist = torch.empty((nq, K), dtype=torch.float32, device="cuda")
+    d_len = torch.empty((nq,), dtype=torch.int32, device="cuda")
+    main = torch.cuda.ExternalStream(shards[0].stream, device=local_rank)
+    torch.cuda.synchronize()
+
+    def step(s):
+        _abi.sharded_search_multi_device(shards, comm, dq_pool[s % len(dq_pool)].data_ptr(), nq, a.ef, K, d_ids.data_ptr(), d_dist.data_ptr(),
+                                         d_len.data_ptr())
+
+    for s in range(a.warmup):
+        step(s)
+    for ix in shards:
+        ix.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.2)
+    barrier(world)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record(main)
+    for s in range(a.warmup, total):
+        step(s)
+    ev1.record(main)
+    ev1.synchronize()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    barrier(world)
+    dev_ms = reduce_max(ev0.elapsed_time(ev1), world)
+    clocks = sampler.summarize(sampler.window(t_wall0, t_wall1))
+    sampler.stop()
+    qps = nq * a.steps / (dev_ms / 1e3)
+    launches = a.steps * (2 * per + (1 if per > 1 else 0) + 2)  # per shard K1 + retry; pre-merge; all-gather; merge
+
+    # K1 of the rank's first sub-index, isolated, for the roofline of the dominant kernel
+    shards[0].search_device(dq_pool[0].data_ptr(), nq, a.ef, K, d_ids.data_ptr(), d_dist.data_ptr(), d_len.data_ptr())
+    k_ms, _ = shards[0].last_kernel_ms()
+    alg = float(algorithmic_bytes(shards[0].last_counters(nq), a.dim, a.M, K).sum())
+    peak, peak_src = measured_peaks()
+
+    # ---- recall@10 of the merged result against the exact top-10 over all N_SUB sub-indexes; protocol + parity checks --------
+    td = np.concatenate([t[0] for t in truth_local], axis=1)
+    ti = np.concatenate([t[1] for t in truth_local], axis=1)
+    sample = a.recall_sample
+    loc = [ix.search(rq, ef_search=a.ef, k=K) for ix in shards]  # per sub-index results (global ids) of the sample
+    keys_loc = np.stack([SH.pack_keys(d_, i_, l_) for (i_, d_, l_) in loc])
+    if world > 1:
+        gt, gk = [None] * world, [None] * world
+        dist.all_gather_object(gt, (td, ti))
+        dist.all_gather_object(gk, keys_loc)
+        td, ti = np.concatenate([g[0] for g in gt], axis=1), np.concatenate([g[1] for g in gt], axis=1)
+        keys_all = np.concatenate(gk, axis=0)
+    else:
+        keys_all = keys_loc
+    order = np.argsort(td, axis=1, kind="stable")[:, :K]
+    truth = np.take_along_axis(ti, order, axis=1)
+    m_ids, m_dist, m_len = _abi.sharded_search_multi(shards, comm, rq, ef_search=a.ef, k=K)  # collective, host buffers
+    recall = recall_at_k(m_ids.astype(np.int64), truth)
+    want_ids, want_dist, want_len = SH.merge_keys(keys_all, K)
+    protocol_ok = bool((m_ids == want_ids).all() and m_dist.tobytes() == want_dist.tobytes() and (m_len == want_len).all())
+    res = {
+        "value": qps, "unit": "queries/s", "n_gpus": world, "ms_per_step": dev_ms / a.steps, "recall_at_10": recall,
+        "merged_eq_protocol": protocol_ok, "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": alg / (k_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (k_ms / 1e3) / 1e9 / peak,
+                     "traffic": None, "kernel": "search_kernel (K1) of one sub-index, isolated launch", "kernel_ms": k_ms,
+                     "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                     "share_of_step": per * k_ms / (dev_ms / a.steps)},
+        "build_s_per_rank": t_build,
+    }
+    if not protocol_ok:
+        log("PROTOCOL FAILURE: the fused sharded search differs from the host statement of the protocol")
+    if full:
+        # e2e: the host-buffer collective, H2D of the batch + D2H of the result inside the timed region
+        hq = [pinned(nq * a.dim * 4, np.float32, (nq, a.dim)) for _ in range(2)]
+        for i, h in enumerate(hq):
+            h[...] = gen(nq, a.dim, 7000 + i)
+        hid, hds, hln = pinned(nq * K * 4, np.uint32, (nq, K)), pinned(nq * K * 4, np.float32, (nq, K)), pinned(nq * 4, np.uint32, (nq,))
+        L = _abi.lib()
+        hs = _abi._handles(shards)
+
+        def e2e_step(s):
+            _abi.check(L.idb_sharded_search_batch_f32_multi(hs, len(shards), comm._h, _abi.ptr(hq[s % 2], C.c_float), nq, a.ef, K,
+                                                            _abi.ptr(hid, C.c_uint32), _abi.ptr(hds, C.c_float), _abi.ptr(hln, C.c_uint32)))
+
+        n_e2e = max(3, a.steps // 2)
+        for s in range(2):
+            e2e_step(s)
+        barrier(world)
+        t0 = time.perf_counter()
+        for s in range(n_e2e):
+            e2e_step(s)
+        e2e_s = reduce_max(time.perf_counter() - t0, world)
+        res["e2e"] = {"value": nq * n_e2e / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * a.dim * 4,
+                      "d2h_bytes_per_step": nq * K * 8 + nq * 4, "steps": n_e2e}
+        # parity of one sub-index against the oracle on that sub-index's graph (rank 0's first)
+        if rank == 0 and not a.skip_cpu_baseline:
+            from oracle import oracle as O
+
+            pp, zz, uu = shards[0].export_graph()
+            ox = O.from_graph(O.Graph(pp, zz, uu, a.M, a.ef))
+            o_ids, o_dist, o_len = ox.search(rq, ef_search=a.ef, k=K, threads=host_threads())
+            l_ids, l_dist, l_len = loc[0]  # the GPU returns global ids (id map): map the oracle's PointIds the same way
+            o_gids = np.where(o_ids == 0xFFFFFFFF, np.uint32(0xFFFFFFFF), gmaps[0][np.minimum(o_ids, a.shard_n - 1)])
+            res["shard0_eq_oracle"] = bool((o_gids == l_ids).all() and (o_len == l_len).all() and o_dist.tobytes() == l_dist.tobytes())
+            if not res["shard0_eq_oracle"]:
+                log("PARITY FAILURE: sub-index 0 on the GPU differs from the oracle on the same graph")
+    for ix in shards:
+        ix.close()
+    comm.close()
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# leg: BASELINE configs[2] — GPU Builder::build (points/s) next to the threaded CPU build of the reference algorithm
+# ---------------------------------------------------------------------------------------------------------------------
+def leg_build(a, local_rank):
+    import torch
+
+    from instant_distance_b200 import _abi
+
+    gen = generator(a.data)
+    pts = gen(a.n, a.dim, 1)
+    times = []
+    ix = None
+    for rep in range(a.build_reps):
+        if ix is not None:
+            ix.close()
+        t = time.perf_counter()
+        ix, ids = _abi.Index.build(pts, M=a.M, ef_construction=a.efc, ef_search=a.ef, seed=a.seed, device=local_rank)
+        times.append(time.perf_counter() - t)
+        log(f"GPU Builder::build {a.n} x {a.dim}, M={a.M}, ef_construction={a.efc}: {times[-1]:.2f}s")
+    rq = gen(a.recall_sample, a.dim, 999)
+    pdev = torch.from_numpy(pts).cuda()
+    truth, _ = brute_force_topk_torch(pdev, rq, K)
+    del pdev
+    inv = np.empty(a.n, dtype=np.int64)
+    inv[ids] = np.arange(a.n)
+    g_ids, _, _ = ix.search(rq, ef_search=a.ef, k=K)
+    recall = recall_at_k(inv[np.minimum(g_ids, a.n - 1)], truth)
+    res = {"metric": "GPU Builder::build throughput", "value": a.n / min(times), "unit": "points/s", "seconds": times,
+           "recall_at_10_of_built_graph": recall, "ef_search": a.ef,
+           "config": {"workload": f"{a.n} x {a.dim} f32 {a.data}-shaped synthetic, M={a.M}, ef_construction={a.efc}"}}
+    if not a.skip_cpu_baseline:
+        from oracle import oracle as O
+
+        T = host_threads()
+        sub = min(a.n, a.build_cpu_sample)
+        t = time.perf_counter()
+        ox, o_ids = O.build(pts[:sub], M=a.M, ef_construction=a.efc, ef_search=a.ef, seed=a.seed, threads=T)
+        dt = time.perf_counter() - t
+        truth_s, _ = O.bruteforce(pts[:sub], rq[:200], K, threads=T)
+        oi, _, _ = ox.search(rq[:200], ef_search=a.ef, k=K, threads=T)
+        inv_s = np.empty(sub, dtype=np.int64)
+        inv_s[o_ids] = np.arange(sub)
+        res["cpu_baseline"] = {"value": sub / dt, "unit": "points/s", "cores": T, "kind": "port",
+                               "sample": f"threaded build (lib.rs:313-318: top layer sequential, the rest parallel with per-row locks) of the first "
+                                         f"{sub} points in {dt:.1f}s; HNSW insert cost grows ~log N, so the full-size rate is lower",
+                               "recall_at_10": recall_at_k(inv_s[oi], truth_s)}
+    ix.close()
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm (CPU only; never imports the CUDA binding)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference(a, rank, world):
     if rank != 0:
         return
     from oracle import oracle as O
 
-    pts, gen = make_workload(args)
-    dev_ok = False
-    try:
-        from instant_distance_b200 import _abi
-
-        dev_ok = _abi.lib().idb_device_count() > 0
-    except Exception:
-        pass
-    if not dev_ok and args.graph == "gpu":
-        args.graph = "oracle"
-    p, zero, upper, how = obtain_graph(args, pts, 0)
-    ix = O.from_graph(O.Graph(p, zero, upper, args.M, args.ef))
     T = host_threads()
-    sample = min(args.batch, args.ref_sample)
-    qs = [gen(sample, args.dim, 1000 + s) for s in range(args.warmup + args.steps)]
-    for s in range(args.warmup):
-        ix.search(qs[s], ef_search=args.ef, k=10, threads=T)
-    t0 = time.perf_counter()
-    for s in range(args.warmup, args.warmup + args.steps):
-        ix.search(qs[s], ef_search=args.ef, k=10, threads=T)
-    dt = time.perf_counter() - t0
-    qps = sample * args.steps / dt
+    if world == 1 or a.mode == "headline":
+        gen = generator(a.data)
+        pts = gen(a.n, a.dim, 1)
+        p, zero, upper, _ = obtain_graph(pts, a.n, a.dim, a.data, 1, a.M, a.efc, a.ef, a.seed, 0, use_abi=False, no_cache=a.no_cache)
+        ix = O.from_graph(O.Graph(p, zero, upper, a.M, a.ef))
+        sample = min(a.batch, a.ref_sample)
+        batches = [gen(sample, a.dim, 5000 + s)[:sample] for s in range(a.warmup + a.steps)]
+        qps, dt = cpu_qps(lambda b: ix.search(b, ef_search=a.ef, k=K, threads=T), batches, a.warmup, a.steps)
+        cfg = search_config(a, 1, "headline")
+        metric = "batched QPS at recall@10>=0.95 (1M x 128 f32)"
+        desc = f"{sample} queries per step x {a.steps} steps after {a.warmup} warm steps, same graph/ef, {T} threads, one Search per thread"
+        scaling = "weak"
+    else:
+        subs = []
+        for s in range(N_SUB):
+            pts = shard_points(a, s)
+            p, zero, upper, ids = obtain_graph(pts, a.shard_n, a.dim, "sift", 1000 + s, a.M, a.efc, a.ef, a.seed + s, 0, use_abi=False,
+                                               no_cache=a.no_cache)
+            gid = np.empty(a.shard_n, dtype=np.uint32)
+            gid[ids] = np.arange(s * a.shard_n, (s + 1) * a.shard_n, dtype=np.uint32)
+            subs.append((O.from_graph(O.Graph(p, zero, upper, a.M, a.ef)), gid))
+        sample = min(a.shard_batch, a.ref_sample_sharded)
+        batches = [datagen.sift_shaped(sample, a.dim, 7000 + s) for s in range(a.warmup + a.steps)]
+
+        def search_all(b):  # every query on every sub-index, then the k smallest (distance, global id) of the union
+            keys = []
+            for ox, gid in subs:
+                i_, d_, l_ = ox.search(b, ef_search=a.ef, k=K, threads=T)
+                g_ = gid[np.minimum(i_, a.shard_n - 1)]
+                kk = (d_.view(np.uint32).astype(np.uint64) << np.uint64(32)) | g_.astype(np.uint64)
+                kk[np.arange(K)[None, :] >= l_[:, None]] = np.uint64(0xFFFFFFFFFFFFFFFF)
+                keys.append(kk)
+            return np.sort(np.concatenate(keys, axis=1), axis=1)[:, :K]
+
+        qps, dt = cpu_qps(search_all, batches, a.warmup, a.steps)
+        cfg = sharded_config(a, world)
+        metric = "batched QPS, 10M x 128 f32 in 8 PointId-range sub-indexes (BASELINE configs[4])"
+        desc = (f"{sample} queries per step x {a.steps} steps after {a.warmup} warm steps, each searched on all {N_SUB} sub-indexes and merged on the "
+                f"host, {T} threads")
+        scaling = "strong"
     line = {
-        "impl": "reference", "metric": "batched QPS at recall@10>=0.95 (1M x 128 f32)", "value": qps, "unit": "queries/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, how),
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": T, "kind": "port",
-                         "sample": f"{sample} queries per step x {args.steps} steps, same graph/ef, {T} threads, one Search per thread"},
+        "impl": "reference", "metric": metric, "value": qps, "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfg, "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": T, "kind": "port", "sample": desc},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_config(args, how):
-    return {"workload": f"{args.n} x {args.dim} f32 {args.data}-shaped synthetic, M={args.M}, ef_construction={args.efc}, "
-                        f"ef_search={args.ef}, batch={args.batch} queries/step, k=10",
-            "graph": how, "l2": "index >> 126 MB L2 and a fresh query batch per step (no flush needed)",
-            "parallelism": f"replica x{args.gpus}, queries sharded" if args.gpus > 1 else "1 GPU"}
 
 
 def main():
@@ -269,6 +750,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "headline", "sharded", "build"])
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--batch", type=int, default=10_000)
@@ -277,19 +759,24 @@ def main():
     ap.add_argument("--M", type=int, default=32)
     ap.add_argument("--seed", type=int, default=20260923)
     ap.add_argument("--data", default="sift", choices=["sift", "uniform"])
-    ap.add_argument("--graph", default="gpu", choices=["gpu", "oracle"])
     ap.add_argument("--no-cache", action="store_true")
     ap.add_argument("--recall-sample", type=int, default=1000)
     ap.add_argument("--ref-sample", type=int, default=10_000)
+    ap.add_argument("--ref-sample-sharded", type=int, default=2_000)
+    ap.add_argument("--shard-n", type=int, default=1_250_000)
+    ap.add_argument("--shard-batch", type=int, default=100_000)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)  # timing rule: at least 3 untimed warm-up steps
+    ap.add_argument("--skip-secondary", action="store_true", help="N=1: headline only (no sharded / uniform legs)")
+    ap.add_argument("--build-reps", type=int, default=2)
+    ap.add_argument("--build-cpu-sample", type=int, default=100_000)
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)  # timing rule: at least 3 untimed warm-up steps
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        return run_reference(args, rank, world)
+    if a.impl == "reference":
+        return run_reference(a, rank, world)
 
     import torch
     import torch.distributed as dist
@@ -301,166 +788,50 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    mode = a.mode if a.mode != "auto" else ("headline" if world == 1 else "sharded")
+    common = {"n_gpus": world, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "f32",
+              "data": "synthetic"}
 
-    if world > 1:
-        args.no_cache = True  # every rank builds its own replica on its own GPU; no shared cache file
-    pts, gen = make_workload(args)
-    p, zero, upper, how = obtain_graph(args, pts, local_rank)
-    ix = _abi.Index.from_graph(p, zero, upper, args.M, args.ef, device=local_rank)
-    ix.set_profiling(True)
-    stream = torch.cuda.ExternalStream(ix.stream, device=local_rank)
-
-    # ---- recall gate: raise ef_search until recall@10 >= 0.95 on a sample --------------------------------------
-    pdev = torch.from_numpy(p).cuda()
-    rq = gen(args.recall_sample, args.dim, 999)
-    truth = brute_force_topk_torch(pdev, rq, 10)
-    del pdev
-    torch.cuda.empty_cache()
-    recall = 0.0
-    for ef in [args.ef, 128, 160, 200, 256, 320, 400, 512]:
-        if ef < args.ef:
-            continue
-        ids, _, _ = ix.search(rq, ef_search=ef, k=10)
-        recall = recall_at_k(ids, truth)
-        log(f"recall@10 = {recall:.4f} at ef_search = {ef}")
-        if recall >= 0.95:
-            args.ef = ef
-            break
-    else:
-        log("WARNING: recall@10 < 0.95 even at ef_search = 512")
-        args.ef = 512
-
-    # ---- device-resident arm ("value") -------------------------------------------------------------------------
-    total = args.warmup + args.steps
-    nq, k = args.batch, 10
-    host_q = [gen(nq, args.dim, 5000 + 977 * rank + s) for s in range(total)]
-    dq = [torch.from_numpy(q).cuda() for q in host_q]
-    d_ids = torch.empty((nq, k), dtype=torch.int32, device="cuda")
-    d_dist = torch.empty((nq, k), dtype=torch.float32, device="cuda")
-    d_len = torch.empty((nq,), dtype=torch.int32, device="cuda")
-    torch.cuda.synchronize()
-
-    def step(s):
-        ix.search_device(dq[s].data_ptr(), nq, args.ef, k, d_ids.data_ptr(), d_dist.data_ptr(), d_len.data_ptr())
-
-    for s in range(args.warmup):
-        step(s)
-    ix.sync()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, launches, alg_bytes = [], 0, []
-    t_wall0 = time.time()
-    ev0.record(stream)
-    for s in range(args.warmup, total):
-        step(s)
-        launches += 2  # K1 search_kernel + its (normally idle) overflow-retry launch; the control-block memset is not a kernel
-    ev1.record(stream)
-    ev1.synchronize()
-    torch.cuda.synchronize()
-    t_wall1 = time.time()
-    if world > 1:
-        dist.barrier()
-    dev_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.summarize(sampler.window(t_wall0, t_wall1))
-
-    # per-launch K1 duration + algorithmic bytes, measured on a second pass (event sync per step would perturb pass 1)
-    for s in range(args.warmup, total):
-        step(s)
-        ms, _ = ix.last_kernel_ms()
-        kernel_ms.append(ms)
-        alg_bytes.append(float(algorithmic_bytes(ix.last_counters(nq), args.dim, args.M, k).sum()))
-
-    if world > 1:
-        t = torch.tensor([dev_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms = float(t.item())
-    qps = world * nq * args.steps / (dev_ms / 1e3)
-
-    # ---- e2e arm: public host API, pinned host buffers, H2D + D2H inside the timed region ----------------------
-    L = _abi.lib()
-
-    def pinned(nbytes, dtype, shape):
-        ptr_ = C.c_void_p()
-        _abi.check(L.idb_host_alloc(nbytes, C.byref(ptr_)))
-        buf = (C.c_char * nbytes).from_address(ptr_.value)
-        return np.frombuffer(buf, dtype=dtype).reshape(shape), ptr_
-
-    # every step's input already sits in its own PINNED host buffer (as the contract describes); results land in pinned buffers
-    hqs = []
-    for s_ in range(total):
-        hq_, _p = pinned(nq * args.dim * 4, np.float32, (nq, args.dim))
-        hq_[...] = host_q[s_]
-        hqs.append((hq_, _p))
-    hid, hid_p = pinned(nq * k * 4, np.uint32, (nq, k))
-    hds, hds_p = pinned(nq * k * 4, np.float32, (nq, k))
-    hln, hln_p = pinned(nq * 4, np.uint32, (nq,))
-
-    def e2e_step(s):
-        _abi.check(L.idb_search_batch_f32(ix._h, _abi.ptr(hqs[s][0], C.c_float), nq, args.ef, k, _abi.ptr(hid, C.c_uint32),
-                                          _abi.ptr(hds, C.c_float), _abi.ptr(hln, C.c_uint32)))
-
-    for s in range(args.warmup):
-        e2e_step(s)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for s in range(args.warmup, total):
-        e2e_step(s)
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_qps = world * nq * args.steps / e2e_s
-    e2e_ids = hid.copy()
-
-    # ---- CPU baseline (rank 0, N=1 leg only) + parity spot check against it --------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.skip_cpu_baseline:  # reported at N=1 only
-        from oracle import oracle as O
-
-        T = host_threads()
-        ox = O.from_graph(O.Graph(p, zero, upper, args.M, args.ef))
-        sample = min(nq, args.ref_sample)
-        qs = host_q[total - 1][:sample]
-        ox.search(qs[:256], ef_search=args.ef, k=k, threads=T)
-        t0 = time.perf_counter()
-        reps = 2
-        for _ in range(reps):
-            o_ids, o_dist, o_len = ox.search(qs, ef_search=args.ef, k=k, threads=T)
-        cdt = time.perf_counter() - t0
-        same = bool((o_ids == e2e_ids[:sample]).all())
-        cpu = {"value": sample * reps / cdt, "unit": "queries/s", "cores": T, "kind": "port",
-               "sample": f"{sample} queries x {reps} passes of the last step's batch, same graph, ef_search={args.ef}, "
-                         f"{T} threads (one Search per thread); GPU ids identical to this run: {same}"}
-        if not same:
-            log("PARITY FAILURE: GPU ids differ from the oracle on the same graph")
-    sampler.stop()
-
-    peak, peak_src = measured_peaks()
-    k_ms = float(np.mean(kernel_ms))
-    ach = float(np.mean(alg_bytes)) / (k_ms / 1e3) / 1e9
-    if rank == 0:
-        line = {
-            "metric": "batched QPS at recall@10>=0.95 (1M x 128 f32)", "value": qps, "unit": "queries/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, how), "recall_at_10": recall, "ef_search": args.ef,
-            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * args.dim * 4,
-                    "d2h_bytes_per_step": nq * k * 8 + nq * 4},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic()[0] if args.n == 1_000_000 and args.dim == 128 and args.batch == 10_000 else None,
-                         "traffic_source": ncu_traffic()[1],
-                         "kernel": "search_kernel (K1 search_layer)", "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_launch": float(np.mean(alg_bytes)), "peak_source": peak_src},
-            "cpu_baseline": cpu, "clocks": clocks,
-        }
-        print(json.dumps(line), flush=True)
+    if mode == "build":
+        res = leg_build(a, local_rank)
+        if rank == 0:
+            print(json.dumps({**res, **common, "scaling": "weak"}), flush=True)
+    elif mode == "headline":
+        h = leg_search(a, rank, local_rank, world)
+        line = {"metric": "batched QPS at recall@10>=0.95 (1M x 128 f32)", "value": h["value"], "unit": "queries/s", **common,
+                "ms_per_step": h["ms_per_step"], "scaling": "weak"}
+        if world == 1 and a.mode == "auto" and not a.skip_secondary:
+            s = leg_sharded(a, rank, local_rank, world, full=False)
+            line["sharded"] = {"what": f"BASELINE configs[4] on ONE GPU ({N_SUB} sub-indexes x {a.shard_n}, batch {a.shard_batch}): the 1-GPU point of the "
+                                       f"strong-scaling curve `--gpus N` reports", "value": s["value"], "unit": "queries/s", "ms_per_step": s["ms_per_step"],
+                               "recall_at_10": s["recall_at_10"], "merged_eq_protocol": s["merged_eq_protocol"], "gpu_launches": s["gpu_launches"],
+                               "k1_frac": s["roofline"]["frac"]}
+        line.update({"config": search_config(a, world, mode), "recall_at_10": h["recall_at_10"], "ef_search": h["ef_search"], "e2e": h.get("e2e"),
+                     "gpu_launches": h["gpu_launches"], "roofline": h["roofline"], "cpu_baseline": h.get("cpu_baseline"), "clocks": h["clocks"]})
+        if world == 1 and a.mode == "auto" and not a.skip_secondary:
+            ua = argparse.Namespace(**{**vars(a), "data": "uniform", "steps": min(a.steps, 10)})
+            u = leg_search(ua, rank, local_rank, world, full=False)
+            line["uniform"] = {"what": "the same kernel on uniform-random 1M x 128 (north_star's wording): no neighbourhood structure, recall@10 stays far "
+                                       "below 0.95 at any practical ef", "value": u["value"], "unit": "queries/s", "recall_at_10": u["recall_at_10"],
+                               "ef_search": u["ef_search"], "k1_frac": u["roofline"]["frac"]}
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+    else:  # sharded
+        s = leg_sharded(a, rank, local_rank, world)
+        line = {"metric": "batched QPS, 10M x 128 f32 in 8 PointId-range sub-indexes (BASELINE configs[4])", "value": s["value"], "unit": "queries/s",
+                **common, "ms_per_step": s["ms_per_step"], "scaling": "strong",
+                "strong_scaling_note": "the 1-GPU point of this curve is `sharded.value` of the --gpus 1 line (same 8 sub-indexes on one GPU); that line's "
+                                       "primary value is configs[1], as the bench contract requires at N=1"}
+        if world > 1 and a.mode == "auto" and not a.skip_secondary:
+            ra = argparse.Namespace(**{**vars(a), "steps": min(a.steps, 10)})
+            r = leg_search(ra, rank, local_rank, world, full=False)
+            line["replicas"] = {"what": "configs[1] with the 1M index replicated per GPU and the queries sharded (no collective)", "value": r["value"],
+                                "unit": "queries/s", "k1_frac": r["roofline"]["frac"], "recall_at_10": r["recall_at_10"]}
+        line.update({"config": sharded_config(a, world), "recall_at_10": s["recall_at_10"], "ef_search": a.ef, "e2e": s.get("e2e"),
+                     "gpu_launches": s["gpu_launches"], "roofline": s["roofline"], "merged_eq_protocol": s["merged_eq_protocol"],
+                     "shard0_eq_oracle": s.get("shard0_eq_oracle"), "cpu_baseline": None, "clocks": s["clocks"]})
+        if rank == 0:
+            print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -195,6 +195,15 @@ IDB_API idb_status idb_sharded_search_batch_f32(idb_index* shard, idb_comm* comm
                                         uint32_t k, uint32_t* out_ids, float* out_dist, uint32_t* out_len);
 IDB_API idb_status idb_sharded_search_batch_device(idb_index* shard, idb_comm* comm, const float* d_queries, uint64_t nq,
                                            uint32_t ef_search, uint32_t k, uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len);
+/* The same for a rank that holds SEVERAL shards on its device (e.g. 8 PointId ranges over 2 or 4 GPUs, or all 8 on one GPU: the
+ * denominator of the 1 -> 8 GPU scaling figure).  The rank's shards are searched concurrently (one launch each, overlapping on the
+ * device), their top-k lists pre-merged on the device, and the rank still contributes ONE k-list per query to the ONE all-gather. */
+IDB_API idb_status idb_sharded_search_batch_f32_multi(idb_index* const* shards, uint32_t n_shards, idb_comm* comm, const float* queries,
+                                              uint64_t nq, uint32_t ef_search, uint32_t k, uint32_t* out_ids, float* out_dist,
+                                              uint32_t* out_len);
+IDB_API idb_status idb_sharded_search_batch_device_multi(idb_index* const* shards, uint32_t n_shards, idb_comm* comm,
+                                                 const float* d_queries, uint64_t nq, uint32_t ef_search, uint32_t k,
+                                                 uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len);
 
 /* The canonical squared-L2 of one pair, evaluated on the device (used by parity tests; FloatArray::distance, py:378-421). */
 IDB_API idb_status idb_distance_f32(const float* a, const float* b, uint32_t dim, int32_t device, float* out);

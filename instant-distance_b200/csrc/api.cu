@@ -33,6 +33,7 @@ cudaError_t dispatch_search_ch3(const SearchArgs&, int, int, int, cudaStream_t, 
 cudaError_t dispatch_search_ch4(const SearchArgs&, int, int, int, cudaStream_t, const LaunchWindow&);
 cudaError_t dispatch_search_ch6(const SearchArgs&, int, int, int, cudaStream_t, const LaunchWindow&);
 cudaError_t dispatch_search_ch8(const SearchArgs&, int, int, int, cudaStream_t, const LaunchWindow&);
+cudaError_t dispatch_search_long(const SearchArgs&, int, int, int, cudaStream_t, const LaunchWindow&);
 
 cudaError_t dispatch_search(const SearchArgs& a, int ch, int row_t, int ef_t, int grid, cudaStream_t st, const LaunchWindow& win) {
     switch (ch) {
@@ -41,7 +42,8 @@ cudaError_t dispatch_search(const SearchArgs& a, int ch, int row_t, int ef_t, in
         case 3: return dispatch_search_ch3(a, row_t, ef_t, grid, st, win);
         case 4: return dispatch_search_ch4(a, row_t, ef_t, grid, st, win);
         case 5: case 6: return dispatch_search_ch6(a, row_t, ef_t, grid, st, win);
-        default: return dispatch_search_ch8(a, row_t, ef_t, grid, st, win);
+        case 7: case 8: return dispatch_search_ch8(a, row_t, ef_t, grid, st, win);
+        default: return dispatch_search_long(a, row_t, ef_t, grid, st, win);
     }
 }
 
@@ -383,7 +385,8 @@ idb_status Index::enqueue_search(Lane& ln, const float* d_queries_padded, uint64
     a.id_map = d_id_map;
 
     const int ch = (int)((nchunks + 31) / 32);
-    if (ch > 8) return fail(IDB_ERR_UNSUPPORTED, "dim %u > 1024 is not supported yet", dim);
+    if (ch > 8 && (nchunks + 31) / 32 * 512 > 40 * 1024)
+        return fail(IDB_ERR_UNSUPPORTED, "dim %u > 10240 is not supported (the query of a long-row traversal lives in shared memory)", dim);
     const int row_t = (int)((2 * M + 31) / 32);
     const int ef_t = (int)((ef + 31) / 32);
     const int grid = std::max(1, (int)std::min<uint64_t>((nq + kSearchWarps - 1) / kSearchWarps, (uint64_t)search_grid()));

@@ -25,6 +25,7 @@ cudaError_t build_dispatch_ch3(const BuildArgs&, const BuildLaunch&, cudaStream_
 cudaError_t build_dispatch_ch4(const BuildArgs&, const BuildLaunch&, cudaStream_t);
 cudaError_t build_dispatch_ch6(const BuildArgs&, const BuildLaunch&, cudaStream_t);
 cudaError_t build_dispatch_ch8(const BuildArgs&, const BuildLaunch&, cudaStream_t);
+cudaError_t build_dispatch_long(const BuildArgs&, const BuildLaunch&, cudaStream_t);
 
 static cudaError_t build_dispatch_any(int ch, const BuildArgs& a, const BuildLaunch& l, cudaStream_t st) {
     switch (ch) {
@@ -33,7 +34,8 @@ static cudaError_t build_dispatch_any(int ch, const BuildArgs& a, const BuildLau
         case 3: return build_dispatch_ch3(a, l, st);
         case 4: return build_dispatch_ch4(a, l, st);
         case 5: case 6: return build_dispatch_ch6(a, l, st);
-        default: return build_dispatch_ch8(a, l, st);
+        case 7: case 8: return build_dispatch_ch8(a, l, st);
+        default: return build_dispatch_long(a, l, st);
     }
 }
 
@@ -369,7 +371,7 @@ extern "C" idb_status idb_build_f32(const float* rows, uint64_t n, uint32_t dim,
     if (n >= 0xFFFFFFFFull) return fail(IDB_ERR_INVALID_ARG, "N = %llu >= u32::MAX (lib.rs:256)", (unsigned long long)n);
     if (params->ef_construction == 0 || params->ef_construction > 1024)
         return fail(IDB_ERR_UNSUPPORTED, "ef_construction = %u unsupported (1..1024)", params->ef_construction);
-    if (dim > 1024) return fail(IDB_ERR_UNSUPPORTED, "dim %u > 1024 is not supported yet", dim);
+    if (dim > 10240) return fail(IDB_ERR_UNSUPPORTED, "dim %u > 10240 is not supported (the owner row of a long-row traversal lives in shared memory)", dim);
     if (!(params->ml > 0.0f) || params->ml >= 1.0f) return fail(IDB_ERR_INVALID_ARG, "ml must be in (0, 1)");
     if (params->storage != IDB_STORAGE_F32 && params->storage != IDB_STORAGE_BF16) return fail(IDB_ERR_INVALID_ARG, "unknown storage %u", params->storage);
     if (params->heuristic && params->extend_candidates)

@@ -17,7 +17,7 @@ struct BuildLaunch {
 
 template <int CH, int ROW_T, int EF_T, int B, class RT>
 cudaError_t launch_insert_search(const BuildArgs& a, const BuildLaunch& l, cudaStream_t st) {
-    const int smem = WarpSmem<EF_T>::kBytes * kSearchWarps;
+    const int smem = (WarpSmem<EF_T>::kBytes + (CH == 0 ? (int)long_q_bytes(a.g.nchunks) : 0)) * kSearchWarps;
     auto kern = insert_search_kernel<CH, ROW_T, EF_T, B, RT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -56,10 +56,20 @@ cudaError_t build_dispatch_rt(const BuildArgs& a, const BuildLaunch& l, cudaStre
             return launch_insert_search<CH, 4, 32, B, RT>(a, l, st);
         case kOpSelectNew:
         case kOpRelink:
-            return l.stage ? launch_k2<CH, NB, true, RT>(a, l, st) : launch_k2<CH, NB, false, RT>(a, l, st);
-        case kOpRelinkSimple:
-            relink_simple_kernel<CH, RT><<<l.grid, kBuildWarps * 32, 0, st>>>(a);
+            if constexpr (CH > 0) {
+                if (l.stage) return launch_k2<CH, NB, true, RT>(a, l, st);
+            }
+            return launch_k2<CH, NB, false, RT>(a, l, st);
+        case kOpRelinkSimple: {
+            const int smem = CH == 0 ? (int)long_q_bytes(a.g.nchunks) * kBuildWarps : 0;
+            auto kern = relink_simple_kernel<CH, RT>;
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                if (e != cudaSuccess) return e;
+            }
+            kern<<<l.grid, kBuildWarps * 32, smem, st>>>(a);
             return cudaGetLastError();
+        }
     }
     return cudaErrorInvalidValue;
 }

@@ -61,7 +61,7 @@ struct BuildArgs {
 template <int CH, int NB, bool kStage, class RT>
 __device__ __forceinline__ uint32_t select_heuristic_warp(const GraphView& g, const uint64_t* cand, uint32_t W, uint32_t* out,
                                                           uint32_t* disc, float4* kept_vecs, uint32_t* kept_pid,
-                                                          bool keep_pruned, int lane) {
+                                                          bool keep_pruned, int lane, QVec<CH>& q, uint64_t* key_scratch) {
     const uint32_t cap = 2 * g.M;
     // warm L2 with every candidate row (each is read once as a "query", kept ones again when not staged)
     {
@@ -70,9 +70,9 @@ __device__ __forceinline__ uint32_t select_heuristic_warp(const GraphView& g, co
             for (uint32_t c = lane; c < W; c += 32) prefetch_l2(g.points + (size_t)key_pid(cand[c]) * rb + ln * 128u);
     }
     uint32_t kept = 0, nd = 0;
-    bool cok[CH];
+    bool cok[CH > 0 ? CH : 1];
 #pragma unroll
-    for (int j = 0; j < CH; ++j) cok[j] = (uint32_t)(lane + 32 * j) < g.nchunks;
+    for (int j = 0; j < (CH > 0 ? CH : 1); ++j) cok[j] = (uint32_t)(lane + 32 * j) < g.nchunks;
     const uint32_t row_bytes = g.nchunks * RT::kChunkBytes;   // global rows (f32 or bf16)
     const uint32_t srow_bytes = g.nchunks * 16u;               // staged rows are always widened float4
     const char* gbase = g.points + lane * RT::kChunkBytes;
@@ -81,15 +81,21 @@ __device__ __forceinline__ uint32_t select_heuristic_warp(const GraphView& g, co
         if (kept >= cap) break;  // lib.rs:669
         const uint64_t ck = cand[i];
         const uint32_t cpid = key_pid(ck), cbits = key_dbits(ck);
-        float4 q[CH];
-        const char* qrow = gbase + (size_t)cpid * row_bytes;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) q[j] = cok[j] ? RT::ld(qrow + j * 32 * RT::kChunkBytes) : make_float4(0.f, 0.f, 0.f, 0.f);
+        q_from_point<CH, RT>(q, g, cpid, lane);  // the candidate is the "query" of the distances below
         bool closer = false;
+        if constexpr (CH == 0) {
+#pragma unroll 1
+            for (uint32_t b0 = 0; b0 < kept && !closer; b0 += kLongRowsInFlight) {
+                const uint32_t nb = min(kept - b0, (uint32_t)kLongRowsInFlight);
+                batch_distances_long<kLongRowsInFlight, RT>(g, q, kept_pid + b0, key_scratch, nb, lane);
+                closer = __any_sync(kFullMask, (uint32_t)lane < nb && key_dbits(key_scratch[lane < kLongRowsInFlight ? lane : 0]) < cbits);
+                __syncwarp();
+            }
+        } else {
 #pragma unroll 1
         for (uint32_t b0 = 0; b0 < kept && !closer; b0 += NB) {
             const uint32_t nb = kept - b0;  // uniform
-            float4 v[NB][CH];
+            float4 v[NB][CH > 0 ? CH : 1];
 #pragma unroll
             for (int r = 0; r < NB; ++r) {
                 const bool ok = (uint32_t)r < nb;  // branch-free: predicated loads, see batch_distances
@@ -102,17 +108,18 @@ __device__ __forceinline__ uint32_t select_heuristic_warp(const GraphView& g, co
             }
             float p[NB];
 #pragma unroll
-            for (int r = 0; r < NB; ++r) p[r] = lane_partial<CH>(q, v[r]);
+            for (int r = 0; r < NB; ++r) p[r] = lane_partial<(CH > 0 ? CH : 1)>(q.r, v[r]);
             const float total = batch_butterfly<NB>(p, lane);
             const bool hit = (uint32_t)lane < nb && lane < NB && canon_bits(total) < cbits;
             closer = __any_sync(kFullMask, hit);
         }
+        }
         if (!closer) {
-            if (kStage) {
+            if constexpr (kStage && CH > 0) {
 #pragma unroll
                 for (int j = 0; j < CH; ++j) {
                     const uint32_t c = lane + 32 * j;
-                    if (c < g.nchunks) kept_vecs[(size_t)kept * g.nchunks + c] = q[j];
+                    if (c < g.nchunks) kept_vecs[(size_t)kept * g.nchunks + c] = q.r[j];
                 }
             }
             if (lane == 0) { out[kept] = cpid; kept_pid[kept] = cpid; }
@@ -142,11 +149,12 @@ struct SelectSmem {
     uint32_t* kept_pid;  // 2M
     uint32_t* cpid;      // 2M + kNewCap   (relink: ids whose distance to the owner is needed)
     uint64_t* ckey;      // 2M + kNewCap
-    float4* kept_vecs;   // 2M x nchunks (kStage only)
+    float4* kept_vecs;   // 2M x nchunks (kStage only) — or, for long rows (CH == 0), the warp's query buffer (long_q_bytes)
     __host__ __device__ static size_t bytes(uint32_t cand_cap, uint32_t M, uint32_t nchunks, bool stage) {
         size_t b = (size_t)cand_cap * 8 + 2 * M * 4 + (size_t)cand_cap * 4 + 2 * M * 4 + (2 * M + kNewCap) * 4 + (2 * M + kNewCap) * 8;
         b = (b + 15) / 16 * 16;
         if (stage) b += (size_t)2 * M * nchunks * 16;
+        else if (nchunks > 256) b += long_q_bytes(nchunks);
         return b;
     }
     __device__ void carve(unsigned char* base, uint32_t cand_cap, uint32_t M, uint32_t nchunks) {
@@ -188,8 +196,9 @@ __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) insert_se
         if (wi >= n_work) break;
         const uint32_t w = a.work_list ? a.work_list[wi] : (uint32_t)wi;
         const uint32_t neu = a.base + w;
-        float4 q[CH];
-        load_row<CH, RT>(a.g, neu, lane, q);
+        QVec<CH> q;
+        long_q_bind<EF_T>(q, smem_raw, a.g.nchunks, warp, kSearchWarps);
+        q_from_point<CH, RT>(q, a.g, neu, lane);
         descend<CH, ROW_T, EF_T, B, false, RT>(a.g, s, q, a.layer, a.efc, lane, nullptr);
         const uint64_t* near = s.near_base + s.cur * s.near_len;
         const uint32_t len = s.status == kQueryOk ? s.cnt : 0u;
@@ -223,8 +232,10 @@ __global__ void __launch_bounds__(kBuildWarps * 32) select_new_kernel(BuildArgs 
         const uint32_t W = a.cand_cnt[w];
         for (uint32_t j = lane; j < W; j += 32) sm.cand[j] = a.cand_keys[(size_t)w * a.cand_cap + j];
         __syncwarp();
+        QVec<CH> q;
+        if constexpr (CH == 0) { q.s = sm.kept_vecs; q.ngroups = (a.g.nchunks + 31) / 32; }
         const uint32_t total = select_heuristic_warp<CH, NB, kStage, RT>(a.g, sm.cand, W, sm.out, sm.disc, sm.kept_vecs, sm.kept_pid,
-                                                                         a.keep_pruned != 0, lane);
+                                                                         a.keep_pruned != 0, lane, q, sm.ckey);
         uint32_t* row = a.zero + (size_t)neu * cap;
         for (uint32_t t = lane; t < cap; t += 32) {
             const uint32_t pid = t < total ? sm.out[t] : kInvalid;
@@ -257,8 +268,8 @@ __global__ void __launch_bounds__(kBuildWarps * 32) relink_kernel(BuildArgs a, u
         uint32_t pos = a.seg_start[w];
         const uint32_t p = (uint32_t)(a.sorted_pairs[pos] >> 32);
         uint32_t* row = a.zero + (size_t)p * cap;
-        float4 q[CH];
-        load_row<CH, RT>(a.g, p, lane, q);
+        QVec<CH> q;
+        if constexpr (CH == 0) { q.s = sm.kept_vecs; q.ngroups = (a.g.nchunks + 31) / 32; }
         for (;;) {  // rounds of at most kNewCap link requests (one round unless p is a hub of this batch)
             // ---- gather: new ids first (push(new), lib.rs:626), then the row's valid prefix (lib.rs:627-629) ----
             uint32_t n_newc = 0;
@@ -276,6 +287,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32) relink_kernel(BuildArgs a, u
             }
             const uint32_t C = n_newc + rcount;
             __syncwarp();
+            q_from_point<CH, RT>(q, a.g, p, lane);  // (per round: select_heuristic below reuses q for the candidates)
             batch_distances<CH, NB, RT>(a.g, q, sm.cpid, sm.ckey, C, lane);
             // ---- push admission (lib.rs:704-720, `nearest` is never truncated here): entry j, in push order, enters
             // iff fewer than ef earlier-pushed entries are smaller (counting earlier REJECTED entries is harmless: a
@@ -311,7 +323,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32) relink_kernel(BuildArgs a, u
             }
             __syncwarp();
             const uint32_t total = select_heuristic_warp<CH, NB, kStage, RT>(a.g, sm.cand, W, sm.out, sm.disc, sm.kept_vecs,
-                                                                             sm.kept_pid, a.keep_pruned != 0, lane);
+                                                                             sm.kept_pid, a.keep_pruned != 0, lane, q, sm.ckey);
             for (uint32_t t = lane; t < cap; t += 32) __stcg(row + t, t < total ? sm.out[t] : kInvalid);  // rewrite
             __threadfence();
             __syncwarp();
@@ -323,7 +335,11 @@ __global__ void __launch_bounds__(kBuildWarps * 32) relink_kernel(BuildArgs a, u
 // per warp, executed in ascending `new` order for every target (a target's requests are serialised by its warp).
 template <int CH, class RT>
 __global__ void __launch_bounds__(kBuildWarps * 32) relink_simple_kernel(BuildArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];  // long rows only: per warp the query buffer
+    __shared__ uint32_t s_pid[kBuildWarps][4];
+    __shared__ uint64_t s_key[kBuildWarps][kLongRowsInFlight];
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const uint32_t cap = 2 * a.g.M;
     const uint32_t n_seg = *a.n_seg;
     for (;;) {
@@ -334,12 +350,24 @@ __global__ void __launch_bounds__(kBuildWarps * 32) relink_simple_kernel(BuildAr
         uint32_t pos = a.seg_start[w];
         const uint32_t p = (uint32_t)(a.sorted_pairs[pos] >> 32);
         uint32_t* row = a.zero + (size_t)p * cap;
-        float4 q[CH];
-        load_row<CH, RT>(a.g, p, lane, q);
+        QVec<CH> q;
+        if constexpr (CH == 0) {
+            q.ngroups = (a.g.nchunks + 31) / 32;
+            q.s = reinterpret_cast<float4*>(smem_raw + (size_t)warp * long_q_bytes(a.g.nchunks));
+        }
+        q_from_point<CH, RT>(q, a.g, p, lane);
         auto dist_to = [&](uint32_t pid) -> uint32_t {  // canonical distance bits from points[p] to points[pid]
-            float4 v[CH];
-            load_row<CH, RT>(a.g, pid, lane, v);
-            return canon_bits(butterfly_sum(lane_partial<CH>(q, v)));
+            if constexpr (CH == 0) {
+                __syncwarp();
+                if (lane == 0) s_pid[warp][0] = pid;
+                __syncwarp();
+                batch_distances_long<kLongRowsInFlight, RT>(a.g, q, s_pid[warp], s_key[warp], 1u, lane);
+                return key_dbits(s_key[warp][0]);
+            } else {
+                float4 v[CH > 0 ? CH : 1];
+                load_row<(CH > 0 ? CH : 1), RT>(a.g, pid, lane, v);
+                return canon_bits(butterfly_sum(lane_partial<(CH > 0 ? CH : 1)>(q.r, v)));
+            }
         };
         while (pos < a.n_pairs_cap && (uint32_t)(a.sorted_pairs[pos] >> 32) == p) {
             const uint32_t neu = (uint32_t)a.sorted_pairs[pos++];

@@ -126,6 +126,48 @@ __device__ __forceinline__ float lane_partial_raw(const float4 (&q)[CH], const t
     return lane_partial<CH>(q, v);
 }
 
+// The query / owner row of a traversal as one lane sees it.  CH >= 1: the lane's CH chunks in registers (rows of up to
+// 128 * CH elements, one kernel instantiation per CH).  CH == 0 ("long rows", any dim): the whole row, widened to f32 and zero
+// padded to a multiple of 32 chunks, in this warp's shared memory; distances then run over groups of 32 chunks in ascending
+// order — the same fmaf chains in the same order as the register flavour (DESIGN.md "canonical distance").
+template <int CH>
+struct QVec {
+    float4 r[CH];
+};
+template <>
+struct QVec<0> {
+    float4* s;         // shared: ngroups * 32 chunks
+    uint32_t ngroups;  // ceil(nchunks / 32)
+};
+constexpr int kLongRowsInFlight = 8;
+// q <- an f32 row of nchunks chunks (a query of the batch)
+template <int CH>
+__device__ __forceinline__ void q_from_f32(QVec<CH>& q, const float4* row, uint32_t nchunks, int lane) {
+    if constexpr (CH == 0) {
+        for (uint32_t c = lane; c < q.ngroups * 32u; c += 32) q.s[c] = c < nchunks ? __ldg(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+    } else {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const uint32_t c = lane + 32 * j;
+            q.r[j] = c < nchunks ? __ldg(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+// q <- point row `pid` (f32 or bf16 storage)
+template <int CH, class RT>
+__device__ __forceinline__ void q_from_point(QVec<CH>& q, const GraphView& g, uint32_t pid, int lane) {
+    if constexpr (CH == 0) {
+        const char* row = g.points + (size_t)pid * (g.nchunks * RT::kChunkBytes);
+        __syncwarp();  // earlier readers of the buffer are done
+        for (uint32_t c = lane; c < q.ngroups * 32u; c += 32)
+            q.s[c] = c < g.nchunks ? RT::ld(row + (size_t)c * RT::kChunkBytes) : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+    } else {
+        load_row<CH, RT>(g, pid, lane, q.r);
+    }
+}
+
 // Butterfly for ONE vector (offsets 1, 2, 4, 8, 16 — the canonical order): every lane ends with the total.
 __device__ __forceinline__ float butterfly_sum(float s) {
 #pragma unroll
@@ -512,10 +554,57 @@ __device__ __forceinline__ void batch_distances_impl(const GraphView& g, const f
     }
     __syncwarp();
 }
+// Long rows (QVec<0>): NB rows in flight per lane and per group of 32 chunks; the accumulators are carried across the groups.
+template <int NB, class RT>
+__device__ __forceinline__ void batch_distances_long(const GraphView& g, const QVec<0>& q, const uint32_t* cpid, uint64_t* ckey,
+                                                     uint32_t n_new, int lane) {
+    const uint32_t row_bytes = g.nchunks * RT::kChunkBytes;
+    const char* lane_base = g.points + lane * RT::kChunkBytes;
+#pragma unroll 1
+    for (uint32_t b0 = 0; b0 < n_new; b0 += NB) {
+        const uint32_t nb = n_new - b0;
+        const char* row[NB];
+        uint64_t a01[NB], a23[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            row[i] = lane_base + (size_t)cpid[b0 + ((uint32_t)i < nb ? i : 0)] * row_bytes;
+            a01[i] = 0ull;
+            a23[i] = 0ull;
+        }
+#pragma unroll 1
+        for (uint32_t j = 0; j < q.ngroups; ++j) {
+            const bool ok = lane + 32u * j < g.nchunks;
+            const float4 qq = q.s[lane + 32u * j];  // zero beyond the row
+            typename RT::Raw v[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) v[i] = (ok && (uint32_t)i < nb) ? RT::ld_raw(row[i] + (size_t)j * 32 * RT::kChunkBytes) : RT::zero();
+            const uint64_t q01 = f32x2_pack(qq.x, qq.y), q23 = f32x2_pack(qq.z, qq.w);
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const float4 w = RT::widen(v[i]);
+                const uint64_t d01 = f32x2_sub(q01, f32x2_pack(w.x, w.y)), d23 = f32x2_sub(q23, f32x2_pack(w.z, w.w));
+                a01[i] = f32x2_fma(d01, d01, a01[i]);
+                a23[i] = f32x2_fma(d23, d23, a23[i]);
+            }
+        }
+        float p[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            float a0, a1, a2, a3;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a01[i]));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(a2), "=f"(a3) : "l"(a23[i]));
+            p[i] = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+        }
+        const float total = batch_butterfly<NB>(p, lane);
+        if ((uint32_t)lane < nb && lane < NB) ckey[b0 + lane] = mk_key(total, cpid[b0 + lane]);
+    }
+    __syncwarp();
+}
 template <int CH, int NB, class RT = RowF32, bool FULL = false>
-__device__ __forceinline__ void batch_distances(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid, uint64_t* ckey,
+__device__ __forceinline__ void batch_distances(const GraphView& g, const QVec<CH>& q, const uint32_t* cpid, uint64_t* ckey,
                                                 uint32_t n_new, int lane) {
-    batch_distances_impl<CH, NB, FULL, RT>(g, q, cpid, ckey, n_new, lane);
+    if constexpr (CH == 0) batch_distances_long<kLongRowsInFlight, RT>(g, q, cpid, ckey, n_new, lane);
+    else batch_distances_impl<CH, NB, FULL, RT>(g, q.r, cpid, ckey, n_new, lane);
 }
 
 // Rare path: something was evicted while its distance equals the new furthest distance.  Such an entry stays a
@@ -602,7 +691,7 @@ __device__ __forceinline__ uint64_t pop_min_tie(WarpState& s, int lane) {
 // read-only/L1 path.
 // ---------------------------------------------------------------------------------------------------------
 template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT, bool FULL>
-__device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, const float4 (&q)[CH], const uint32_t* rows,
+__device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, const QVec<CH>& q, const uint32_t* rows,
                                              uint32_t width, uint32_t links, uint32_t ef_cur, bool seed_entry, int lane) {
     const uint32_t lt_mask = (1u << lane) - 1;
     for (;;) {
@@ -832,7 +921,7 @@ __device__ __forceinline__ void cull(WarpState& s, int lane, bool next_big) {
 // Layers above the target are searched on the UpperNode snapshots with ef = 1; the target layer on the zero table.
 // On return nearest = (s.near_base + s.cur * s.near_len)[0..s.cnt).  counters (if non-null): {n_expand_upper, n_dist_upper, n_expand_target, n_dist_target}.
 template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT = RowF32, bool FULL = false>
-__device__ __forceinline__ void descend(const GraphView& g, WarpState& s, const float4 (&q)[CH], uint32_t target_layer,
+__device__ __forceinline__ void descend(const GraphView& g, WarpState& s, const QVec<CH>& q, uint32_t target_layer,
                                         uint32_t ef_target, int lane, uint32_t* counters4) {
     s.cur = 0;
     s.cnt = 0;

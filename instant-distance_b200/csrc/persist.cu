@@ -78,7 +78,7 @@ idb_status idb_index_load(const char* path, uint32_t dim, uint32_t M, int32_t de
     std::fseek(in.f, 0, SEEK_SET);
     uint64_t ef = 0, n = 0, n2 = 0, nl = 0;
     if (!get_u64(in.f, &ef) || !get_u64(in.f, &n)) return fail(IDB_ERR_FORMAT, "%s: truncated header", path);
-    if (n >= 0xFFFFFFFFull || 16 + n * dim * 4 > fsize) return fail(IDB_ERR_FORMAT, "%s: point count %llu does not fit the file (dim %u?)", path, (unsigned long long)n, dim);
+    if (n >= 0xFFFFFFFFull || fsize < 16 || n > (fsize - 16) / ((uint64_t)dim * 4)) return fail(IDB_ERR_FORMAT, "%s: point count %llu does not fit the file (dim %u?)", path, (unsigned long long)n, dim);
     std::vector<float> pts((size_t)n * dim);
     if (!get(in.f, pts.data(), pts.size() * 4) || !get_u64(in.f, &n2) || n2 != n)
         return fail(IDB_ERR_FORMAT, "%s: zero-layer length does not match the point count (wrong dim?)", path);
@@ -99,8 +99,10 @@ idb_status idb_index_load(const char* path, uint32_t dim, uint32_t M, int32_t de
     if (out_values_offset) *out_values_offset = (uint64_t)std::ftell(in.f);
     for (uint32_t v : zero)
         if (v != IDB_INVALID && v >= n) return fail(IDB_ERR_FORMAT, "%s: adjacency refers to PointId %u >= %llu", path, v, (unsigned long long)n);
-    return idb_index_from_graph_f32(pts.data(), n, dim, M, (uint32_t)std::min<uint64_t>(ef, 0xFFFFFFFFu), zero.data(), (uint32_t)nl,
-                                    ptrs.data(), counts.data(), device, out_index);
+    // the same checks as for any adopted graph (entries inside their layer, n >= n_1 >= ... >= 1); a file that fails them is malformed
+    const idb_status st = idb_index_from_graph_f32(pts.data(), n, dim, M, (uint32_t)std::min<uint64_t>(ef, 0xFFFFFFFFu), zero.data(),
+                                                   (uint32_t)nl, ptrs.data(), counts.data(), device, out_index);
+    return st == IDB_ERR_INVALID_ARG ? IDB_ERR_FORMAT : st;
 }
 
 }  // extern "C"

@@ -26,6 +26,15 @@ struct WarpSmem {
         s.vis.hist = reinterpret_cast<uint32_t*>(s.ckey);  // 256 words, only live between a row load and its distances
     }
 };
+// Long rows (CH == 0): the warps' query buffers follow the per-warp traversal state in dynamic shared memory.
+__host__ __device__ inline uint32_t long_q_bytes(uint32_t nchunks) { return (nchunks + 31) / 32 * 32 * 16; }
+template <int EF_T, int CH>
+__device__ __forceinline__ void long_q_bind(QVec<CH>& q, unsigned char* smem_raw, uint32_t nchunks, int warp, int warps_per_cta) {
+    if constexpr (CH == 0) {
+        q.ngroups = (nchunks + 31) / 32;
+        q.s = reinterpret_cast<float4*>(smem_raw + (size_t)warps_per_cta * WarpSmem<EF_T>::kBytes + (size_t)warp * long_q_bytes(nchunks));
+    }
+}
 // Point the warp at its claimed scratch tables.
 __device__ __forceinline__ void bind_tables(WarpState& s, const TablePool& tp, uint32_t table, uint32_t gslots, uint32_t gshift,
                                             uint32_t mode, uint32_t cap_ids) {
@@ -64,13 +73,9 @@ __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchAr
         if (w >= n_work) break;
         const uint64_t qi = a.work_list ? a.work_list[w] : w;
 
-        float4 q[CH];
-        const float4* qrow = a.queries + qi * a.g.nchunks;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            const uint32_t c = lane + 32 * j;
-            q[j] = c < a.g.nchunks ? __ldg(qrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        QVec<CH> q;
+        long_q_bind<EF_T>(q, smem_raw, a.g.nchunks, warp, kSearchWarps);
+        q_from_f32<CH>(q, a.queries + qi * a.g.nchunks, a.g.nchunks, lane);
 
         descend<CH, ROW_T, EF_T, B, false, RT, FULL>(a.g, s, q, 0u, a.ef, lane, a.counters ? a.counters + qi * 4 : nullptr);
 
@@ -122,7 +127,7 @@ static cudaError_t launch_with_window(Kern kern, int grid, int block, int smem, 
 
 template <int CH, int ROW_T, int EF_T, int B, int OCC = kSearchCtasPerSm, class RT = RowF32, bool FULL = false>
 static cudaError_t launch_search(const SearchArgs& a, int grid, cudaStream_t stream, const LaunchWindow& win) {
-    const int smem = WarpSmem<EF_T>::kBytes * kSearchWarps;
+    const int smem = (WarpSmem<EF_T>::kBytes + (CH == 0 ? (int)long_q_bytes(a.g.nchunks) : 0)) * kSearchWarps;
     auto kern = search_kernel<CH, ROW_T, EF_T, B, OCC, RT, FULL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -131,7 +136,9 @@ static cudaError_t launch_search(const SearchArgs& a, int grid, cudaStream_t str
 
 template <int CH, int ROW_T, int EF_T, int B, class RT>
 cudaError_t launch_search_full(const SearchArgs& a, int grid, cudaStream_t st, const LaunchWindow& win) {
-    if (a.g.nchunks == 32u * CH) return launch_search<CH, ROW_T, EF_T, B, kSearchCtasPerSm, RT, true>(a, grid, st, win);
+    if constexpr (CH > 0) {
+        if (a.g.nchunks == 32u * CH) return launch_search<CH, ROW_T, EF_T, B, kSearchCtasPerSm, RT, true>(a, grid, st, win);
+    }
     return launch_search<CH, ROW_T, EF_T, B, kSearchCtasPerSm, RT, false>(a, grid, st, win);
 }
 template <int CH, int B, class RT>

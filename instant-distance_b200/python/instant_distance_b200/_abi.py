@@ -22,7 +22,7 @@ SYMBOLS = [
     "idb_index_export_zero", "idb_index_export_upper", "idb_index_save", "idb_index_load", "idb_index_set_profiling", "idb_index_last_kernel_ms", "idb_debug_gather_bench", "idb_debug_gather_mix_bench",
     "idb_index_stream", "idb_index_sync", "idb_index_free",
     "idb_comm_unique_id", "idb_comm_create", "idb_comm_free", "idb_index_set_id_map", "idb_sharded_search_batch_f32",
-    "idb_sharded_search_batch_device", "idb_distance_f32", "idb_host_alloc", "idb_host_free", "idb_last_error", "idb_version", "idb_device_count",
+    "idb_sharded_search_batch_device", "idb_sharded_search_batch_f32_multi", "idb_sharded_search_batch_device_multi", "idb_distance_f32", "idb_host_alloc", "idb_host_free", "idb_last_error", "idb_version", "idb_device_count",
 ]
 
 
@@ -97,6 +97,8 @@ def lib():
     L.idb_index_set_id_map.argtypes = [vp, u32p]
     L.idb_sharded_search_batch_f32.argtypes = [vp, vp, f32p, C.c_uint64, C.c_uint32, C.c_uint32, u32p, f32p, u32p]
     L.idb_sharded_search_batch_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp]
+    L.idb_sharded_search_batch_f32_multi.argtypes = [C.POINTER(vp), C.c_uint32, vp, f32p, C.c_uint64, C.c_uint32, C.c_uint32, u32p, f32p, u32p]
+    L.idb_sharded_search_batch_device_multi.argtypes = [C.POINTER(vp), C.c_uint32, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp]
     L.idb_distance_f32.argtypes = [f32p, f32p, C.c_uint32, C.c_int32, f32p]
     L.idb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.idb_host_free.argtypes = [vp]
@@ -335,6 +337,27 @@ class Comm:
             self.close()
         except Exception:  # noqa: BLE001  (interpreter shutdown)
             pass
+
+
+def _handles(shards):
+    return (C.c_void_p * len(shards))(*[s._h for s in shards])
+
+
+def sharded_search_multi(shards, comm, queries, ef_search=0, k=10):
+    """Collective: this rank's shards (all on one device) + ONE all-gather over `comm`.  Host buffers."""
+    q = shards[0]._queries(queries)
+    nq = q.shape[0]
+    ids = np.empty((nq, k), dtype=np.uint32)
+    dist = np.empty((nq, k), dtype=np.float32)
+    lens = np.empty(nq, dtype=np.uint32)
+    check(lib().idb_sharded_search_batch_f32_multi(_handles(shards), len(shards), comm._h, ptr(q, C.c_float), nq, ef_search, k,
+                                                   ptr(ids, C.c_uint32), ptr(dist, C.c_float), ptr(lens, C.c_uint32)))
+    return ids, dist, lens
+
+
+def sharded_search_multi_device(shards, comm, d_queries, nq, ef_search, k, d_ids, d_dist, d_len):
+    """Device pointers; enqueues on lane 0 of shards[0] (every shard's stream is joined into it) and returns."""
+    check(lib().idb_sharded_search_batch_device_multi(_handles(shards), len(shards), comm._h, d_queries, nq, ef_search, k, d_ids, d_dist, d_len))
 
 
 def distance(a, b, device=0):

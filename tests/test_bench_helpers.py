@@ -29,9 +29,19 @@ def test_committed_ncu_traffic_is_consistent():
     assert os.path.exists(os.path.join(bench.ROOT, source.split(" ")[0]))  # the summary the figure was read from is committed
 
 
-def test_workload_config_names_the_baseline_config():
+def test_configs_name_the_baseline_configs_and_match_across_arms():
     class A:
-        n, dim, data, M, efc, ef, batch, gpus = 1_000_000, 128, "sift", 32, 100, 100, 10_000, 1
+        n, dim, data, M, efc, ef, batch, gpus, shard_n, shard_batch = 1_000_000, 128, "sift", 32, 100, 100, 10_000, 1, 1_250_000, 100_000
 
-    cfg = bench.workload_config(A, "GPU Builder::build")
+    cfg = bench.search_config(A, 1, "headline")
     assert "1000000 x 128" in cfg["workload"] and "ef_search=100" in cfg["workload"] and cfg["parallelism"] == "1 GPU"
+    # no timings / cache markers inside config: both arms of a run print the identical object
+    assert cfg == bench.search_config(A, 1, "headline") and "cached" not in json.dumps(cfg) and "(s)" not in cfg["graph"]
+    sh = bench.sharded_config(A, 8)
+    assert "8 x 1250000 = 10000000 x 128" in sh["workload"] and "batch=100000" in sh["workload"] and "ONE ncclAllGather" in sh["parallelism"]
+
+
+def test_cpu_baseline_protocol_counts_only_the_timed_passes():
+    calls = []
+    qps, dt = bench.cpu_qps(lambda b: calls.append(len(b)), [np.zeros((7, 2))] * 6, 2, 4)
+    assert calls == [7] * 6 and dt > 0 and abs(qps - 28 / dt) < 1e-6 * qps

@@ -22,7 +22,7 @@ def abi():
     return _abi
 
 
-@pytest.mark.parametrize("n,dim,M,ef", [(4000, 128, 32, 100), (3000, 300, 24, 64), (2000, 768, 32, 128), (3000, 30, 16, 200)])
+@pytest.mark.parametrize("n,dim,M,ef", [(4000, 128, 32, 100), (3000, 300, 24, 64), (2000, 768, 32, 128), (3000, 30, 16, 200), (1200, 1536, 32, 64)])
 def test_bf16_search_parity(abi, oracle, n, dim, M, ef):
     pts = datagen.uniform(n, dim, 31)
     rp = bf16_round(pts)
@@ -54,7 +54,7 @@ def test_bf16_rounds_on_upload(abi, oracle):
     assert (a[0] == b[0]).all() and a[1].tobytes() == b[1].tobytes()
 
 
-@pytest.mark.parametrize("n,dim", [(1500, 128), (1000, 768)])
+@pytest.mark.parametrize("n,dim", [(1500, 128), (1000, 768), (500, 1536)])
 def test_bf16_sequential_build_equals_oracle_on_rounded_points(abi, oracle, n, dim):
     pts = datagen.uniform(n, dim, 8)
     ix_o, ids_o = oracle.build(bf16_round(pts), seed=12, threads=1)

@@ -271,3 +271,17 @@ def test_rows_with_repeated_ids(abi, oracle, monkeypatch, flavour):
     g2 = oracle.Graph(g.points, zero, g.upper, g.M, g.ef_search)
     ix2 = oracle.from_graph(g2)
     _check(abi, oracle, g2, ix2, datagen.uniform(400, 24, 6), 100)
+
+
+def test_search_parity_oracle_built_200k_sift(abi, oracle):
+    """BASELINE configs[1] says "search on reference-built graph": here a 200 000 x 128 sift-shaped graph built by the reference
+    ALGORITHM (the oracle's threaded build, lib.rs:313-318) — not by this library — searched by both at the config's ef_search=100
+    with 5 000 queries: ids, distances, len(nearest) and the per-layer traversal counters must all be bit-identical."""
+    import os
+
+    pts = datagen.sift_shaped(200_000, 128, 1)
+    ix, _ = oracle.build(pts, seed=20260923, threads=min(32, os.cpu_count() or 8))
+    g = ix.export()
+    assert ix.num_layers == 8 and ix.layer_counts()[0] == 200_000
+    _check(abi, oracle, g, ix, datagen.sift_shaped(5000, 128, 2), 100, k=100)
+    _check(abi, oracle, g, ix, datagen.sift_shaped(2000, 128, 3), 200, k=10)
