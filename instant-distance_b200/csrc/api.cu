@@ -112,6 +112,8 @@ __global__ void repeated_ids_kernel(const uint32_t* rows, size_t n_rows, uint32_
     }
 }
 
+__global__ void nsmid_kernel(uint32_t* out) { asm volatile("mov.u32 %0, %%nsmid;" : "=r"(*out)); }
+
 __global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -172,8 +174,8 @@ TablePool DeviceCtx::main_pool(bool b16) const {
 TablePool DeviceCtx::retry_pool() const {
     TablePool tp;
     tp.slot_masks = slot_masks;
-    tp.fixed_word = num_sms;
-    tp.word_base = (uint32_t)num_sms;
+    tp.fixed_word = sm_ids;
+    tp.word_base = (uint32_t)sm_ids;
     tp.slots_per_word = kRetryCtas;
     tp.vis_tables = retry_tables;
     tp.vis_stride = kRetrySlots;
@@ -203,17 +205,29 @@ idb_status DeviceCtx::acquire(int device, DeviceCtx** out) {
     CTX_TRY(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
     if (const char* e = std::getenv("IDB_CTAS_PER_SM")) c->slots_per_sm = std::min(kMaxCtasPerSm, std::max(1, std::atoi(e)));
-    c->n_tables = (uint32_t)c->num_sms * (uint32_t)c->slots_per_sm * kSearchWarps;
+    {   // SM ids run up to %nsmid, which counts disabled SMs too
+        uint32_t* d = nullptr;
+        uint32_t h = 0;
+        CTX_TRY(cudaMalloc(&d, 4));
+        nsmid_kernel<<<1, 1>>>(d);
+        cudaError_t e1 = cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost);
+        cudaFree(d);
+        CTX_TRY(e1);
+        c->sm_ids = std::max<int>((int)h, c->num_sms);
+    }
+    c->n_tables = (uint32_t)c->sm_ids * (uint32_t)c->slots_per_sm * kSearchWarps;
+    c->n_tables_live = (uint32_t)c->num_sms * (uint32_t)c->slots_per_sm * kSearchWarps;
     cudaDeviceGetAttribute(&c->max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
     cudaDeviceGetAttribute(&c->max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
     c->l2_allowed = g_l2_pref[device] >= 0;
     if (const char* e = std::getenv("IDB_L2_PERSIST")) c->l2_allowed = c->l2_allowed && std::atoi(e) != 0;
     // b16 tables: as many bytes per warp as keep ALL tables inside the persisting part of L2 (34 KB on B200: 79 MB / 2368 warps)
-    size_t per = c->max_persist > 0 ? (size_t)c->max_persist / c->n_tables : (size_t)32 * 1024;
-    per = std::min<size_t>(std::max<size_t>(per / 512 * 512, 8 * 1024), 64 * 1024);
+    // (at most 32 KB = 1024 buckets: the per-row tally of the b16 flavour has one byte per bucket in 1 KB of shared memory)
+    size_t per = c->max_persist > 0 ? (size_t)c->max_persist / c->n_tables_live : (size_t)32 * 1024;
+    per = std::min<size_t>(std::max<size_t>(per / 512 * 512, 8 * 1024), 32 * 1024);
     c->b16_stride = (uint32_t)(per / 4);
-    CTX_TRY(cudaMalloc(&c->slot_masks, ((size_t)c->num_sms + 1) * 4));
-    CTX_TRY(cudaMemset(c->slot_masks, 0, ((size_t)c->num_sms + 1) * 4));
+    CTX_TRY(cudaMalloc(&c->slot_masks, ((size_t)c->sm_ids + 1) * 4));
+    CTX_TRY(cudaMemset(c->slot_masks, 0, ((size_t)c->sm_ids + 1) * 4));
     CTX_TRY(cudaMalloc(&c->b16_tables, (size_t)c->n_tables * per));
     CTX_TRY(cudaMemset(c->b16_tables, 0xFF, (size_t)c->n_tables * per));
     const size_t retry_words = (size_t)kRetryCtas * kSearchWarps * kRetrySlots;
@@ -330,7 +344,7 @@ idb_status Index::select_visited_tier(uint32_t ef, SearchArgs& a, LaunchWindow& 
         a.gshift = 0;
         a.vis_mode = kVisB16;
         a.b16_cap_ids = nb * 11;  // <= 11 of 16 slots on average; fuller tables hand the query to the retry pass
-        idb_status st = c.reserve_l2((size_t)c.n_tables * b16_bytes);
+        idb_status st = c.reserve_l2((size_t)c.n_tables_live * b16_bytes);
         if (st != IDB_OK) return st;
         if (c.l2_reserved) {
             win.base = c.b16_tables;

@@ -231,7 +231,8 @@ struct VisitedSet {
     uint32_t nb;       // b16 flavour: buckets in use
     float nb_inv;      // 1 / nb
     uint32_t cap_ids;  // b16 flavour: ids the table may hold before the query is handed to the retry pass
-    uint32_t* hist;    // shared, 256 words: per-row slot bookkeeping of the b16 flavour (aliases WarpState::ckey, dead in that phase)
+    uint32_t* hist;    // shared, 256 words = 1024 one-byte tallies, one per bucket: slots handed out since the snapshots of the current row
+                       // were taken (b16 flavour; aliases WarpState::ckey, dead in that phase) — hence at most 1024 buckets per table
 };
 // Big-tier flavours, all exact:
 //   kVisHash    open addressing, one u32 slot per id, atomicCAS + linear probing (any n; the retry pass and the fallback)
@@ -276,8 +277,8 @@ __device__ __forceinline__ uint32_t vis_bitmap_fetch_clear(uint32_t* tab, uint32
 //   * an id lives in its home bucket if that bucket had a free slot when the id was inserted, else (flagged "displaced") in the
 //     next bucket; so "not in the home bucket, and the home bucket still has a free slot" proves absence with ONE 32-byte read;
 //   * the warp owns the table: concurrent inserts only ever come from lanes of this warp handling the same adjacency row, and
-//     those are arbitrated in registers (match_any on the home bucket + a 256-entry shared-memory tally for row entries that
-//     live in different registers), so inserts are plain stores and nobody waits for them.
+//     those are arbitrated in registers (match_any on the home bucket) plus an exact per-bucket tally in shared memory (one byte
+//     per bucket) for row entries that live in different registers, so inserts are plain stores and nobody waits for them.
 //   * PointIds within one adjacency row are distinct (true for every graph this library or the reference builds; adopted graphs
 //     are checked at upload and fall back to the atomic flavours if a row repeats an id).
 struct Bucket8 { uint4 lo, hi; };
@@ -330,6 +331,12 @@ __device__ __forceinline__ uint32_t b16_count(const Bucket8& k) {
     }
     return 16u - __popc(m);
 }
+// Per-bucket tally (one byte per bucket, <= 1024 buckets): how many slots of bucket b were handed out since the current row's
+// snapshots were taken.  <= 128 per row (4 registers x 32 lanes), so a byte never carries into its neighbour.
+__device__ __forceinline__ uint32_t b16_tally_add(VisitedSet& v, uint32_t b, uint32_t n) {
+    const uint32_t sh = 8u * (b & 3u);
+    return (atomicAdd(&v.hist[b >> 2], n << sh) >> sh) & 0xFFu;
+}
 // Exact insert by ONE lane on fresh data (the others wait): 1 inserted, 0 already there, 2 no room within two buckets.
 __device__ __forceinline__ uint32_t b16_insert_slow(VisitedSet& v, B16 t) {
     uint32_t b = t.home, val = t.tag;
@@ -339,7 +346,7 @@ __device__ __forceinline__ uint32_t b16_insert_slow(VisitedSet& v, B16 t) {
         const uint32_t cnt = b16_count(k);
         if (cnt < 16u) {
             b16_store(v.big, b, cnt, val);
-            atomicAdd(&v.hist[b & 255u], 1u);  // row entries in other registers hold an older snapshot of this bucket
+            b16_tally_add(v, b, 1u);  // row entries in other registers hold an older snapshot of this bucket
             return 1u;
         }
         if (step == 1 || t.tag == 0x7FFFu) return 2u;  // 0x8000 | 0x7FFF is the EMPTY pattern: cannot be stored displaced
@@ -361,7 +368,7 @@ __device__ __forceinline__ bool b16_commit(VisitedSet& v, B16 tg, const Bucket8&
     const uint32_t peers = __match_any_sync(kFullMask, isnew ? tg.home : (0x80000000u | (uint32_t)lane));
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
-    if (isnew && lane == leader) base = atomicAdd(&v.hist[tg.home & 255u], (uint32_t)__popc(peers));
+    if (isnew && lane == leader) base = b16_tally_add(v, tg.home, (uint32_t)__popc(peers));
     base = __shfl_sync(kFullMask, base, leader);
     if (isnew) {
         const uint32_t pos = cnt + base + __popc(peers & ((1u << lane) - 1u));
@@ -382,7 +389,7 @@ __device__ __forceinline__ bool b16_commit(VisitedSet& v, B16 tg, const Bucket8&
     __syncwarp();
     return isnew;
 }
-__device__ __forceinline__ void b16_tally_reset(VisitedSet& v, B16 tg) { v.hist[tg.home & 255u] = 0u; }
+__device__ __forceinline__ void b16_tally_reset(VisitedSet& v, B16 tg) { reinterpret_cast<unsigned char*>(v.hist)[tg.home] = 0; }
 
 // One id per lane into the big tier, any flavour.  Warp-uniform call (the b16 flavour is cooperative).
 __device__ __forceinline__ bool vis_insert_big_any(VisitedSet& v, uint32_t pid, bool want, int lane, bool* ovf) {
@@ -487,6 +494,10 @@ struct WarpState {
     uint64_t* ckey;          // shared: their 128 keys (canonical distance bits << 32 | pid)
     uint64_t* ties;          // global: tie_cap keys
     uint32_t tie_cap;
+    // EXPERIMENT (profiles/r02_experiment_tma_ring.md): point rows staged in a per-warp shared-memory ring by cp.async.bulk
+    char* ring;              // shared: B rows of nchunks * 16 bytes
+    uint64_t* mbar;          // shared: the ring's mbarrier
+    uint32_t mbar_phase;
     int cur;                 // live near buffer
     uint32_t cnt;            // len(nearest)
     uint32_t ntie;
@@ -607,6 +618,16 @@ __device__ __forceinline__ void batch_distances(const GraphView& g, const QVec<C
     else batch_distances_impl<CH, NB, FULL, RT>(g, q.r, cpid, ckey, n_new, lane);
 }
 
+// EXPERIMENT — the TMA staging north_star describes: every point row of a batch is fetched by ONE cp.async.bulk (1-D bulk copy,
+// global -> shared, completion counted on an mbarrier) into a per-warp ring; no register staging (the 16 x float4 landing registers
+// of batch_distances_impl are gone: more warps fit), distances computed from shared memory.  f32 rows only.  Same arithmetic and
+// summation order as batch_distances_impl, so results are bit-identical.  Measured against the register-gather K1 in
+// profiles/r02_experiment_tma_ring.md; selected with IDB_VARIANT 5..7.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+struct WarpState;
+template <int CH, int NB>
+__device__ __forceinline__ void batch_distances_tma(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid, uint64_t* ckey,
+                                                    uint32_t n_new, int lane, WarpState& s);
 // Rare path: something was evicted while its distance equals the new furthest distance.  Such an entry stays a
 // live candidate in the reference (strict `>` at lib.rs:601) iff it is unexpanded and had been ADMITTED
 // (pushed on `candidates`, lib.rs:719).  Admission of row entry j: rank_S(j) + #{i<j in row order, i in A, key_i < key_j} < ef.
@@ -681,6 +702,47 @@ __device__ __forceinline__ uint64_t pop_min_tie(WarpState& s, int lane) {
     return best;
 }
 
+template <int CH, int NB>
+__device__ __forceinline__ void batch_distances_tma(const GraphView& g, const float4 (&q)[CH], const uint32_t* cpid, uint64_t* ckey,
+                                                    uint32_t n_new, int lane, WarpState& s) {
+    const uint32_t row_bytes = g.nchunks * 16u;
+    const uint32_t bar = smem_addr(s.mbar);
+#pragma unroll 1
+    for (uint32_t b0 = 0; b0 < n_new; b0 += NB) {
+        const uint32_t nb = min(n_new - b0, (uint32_t)NB);
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb * row_bytes) : "memory");
+        if ((uint32_t)lane < nb) {  // one bulk copy per row, issued by the lane of the same index
+            const char* src = g.points + (size_t)cpid[b0 + lane] * row_bytes;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_addr(s.ring + (size_t)lane * row_bytes)),
+                         "l"(src), "r"(row_bytes), "r"(bar)
+                         : "memory");
+        }
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done)
+                         : "r"(bar), "r"(s.mbar_phase)
+                         : "memory");
+        s.mbar_phase ^= 1u;
+        float p[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            float4 v[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const uint32_t c = lane + 32 * j;
+                v[j] = ((uint32_t)i < nb && c < g.nchunks) ? *reinterpret_cast<const float4*>(s.ring + (size_t)i * row_bytes + c * 16u)
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            p[i] = lane_partial<CH>(q, v);
+        }
+        const float total = batch_butterfly<NB>(p, lane);
+        if ((uint32_t)lane < nb && lane < NB) ckey[b0 + lane] = mk_key(total, cpid[b0 + lane]);
+        __syncwarp();  // every lane has read the ring before the next batch's copies overwrite it
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // search_layer (lib.rs:598-614) over one layer.
 //   rows/width : adjacency table of this layer (fixed stride `width` u32 per node)
@@ -690,7 +752,7 @@ __device__ __forceinline__ uint64_t pop_min_tie(WarpState& s, int lane) {
 // kLive: rows may be rewritten concurrently (GPU build) -> read them through L2 (ld.global.cg), not the
 // read-only/L1 path.
 // ---------------------------------------------------------------------------------------------------------
-template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT, bool FULL>
+template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT, bool FULL, bool TMA = false>
 __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, const QVec<CH>& q, const uint32_t* rows,
                                              uint32_t width, uint32_t links, uint32_t ef_cur, bool seed_entry, int lane) {
     const uint32_t lt_mask = (1u << lane) - 1;
@@ -799,7 +861,8 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
         }
 
         // ---- distances (lib.rs:709-710) --------------------------------------------------------------------
-        batch_distances<CH, B, RT, FULL>(g, q, s.cpid, s.ckey, n_new, lane);
+        if constexpr (TMA) batch_distances_tma<CH, B>(g, q.r, s.cpid, s.ckey, n_new, lane, s);
+        else batch_distances<CH, B, RT, FULL>(g, q, s.cpid, s.ckey, n_new, lane);
         uint64_t keyg[ROW_T];
 #pragma unroll
         for (int gi = 0; gi < ROW_T; ++gi) {
@@ -920,7 +983,7 @@ __device__ __forceinline__ void cull(WarpState& s, int lane, bool next_big) {
 // Construction::insert's descent (lib.rs:443-463) when target_layer = the insert layer, ef_target = ef_construction.
 // Layers above the target are searched on the UpperNode snapshots with ef = 1; the target layer on the zero table.
 // On return nearest = (s.near_base + s.cur * s.near_len)[0..s.cnt).  counters (if non-null): {n_expand_upper, n_dist_upper, n_expand_target, n_dist_target}.
-template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT = RowF32, bool FULL = false>
+template <int CH, int ROW_T, int EF_T, int B, bool kLive, class RT = RowF32, bool FULL = false, bool TMA = false>
 __device__ __forceinline__ void descend(const GraphView& g, WarpState& s, const QVec<CH>& q, uint32_t target_layer,
                                         uint32_t ef_target, int lane, uint32_t* counters4) {
     s.cur = 0;
@@ -939,7 +1002,7 @@ __device__ __forceinline__ void descend(const GraphView& g, WarpState& s, const 
         const uint32_t* rows = above ? g.upper[cur - 1] : g.zero;
         const uint32_t width = above ? g.M : 2 * g.M;
         const uint32_t links = (above || target_layer != 0) ? g.M : 2 * g.M;  // lib.rs:445 / 366-369
-        search_layer<CH, ROW_T, EF_T, B, kLive, RT, FULL>(g, s, q, rows, width, links, above ? 1u : ef_target, seed, lane);
+        search_layer<CH, ROW_T, EF_T, B, kLive, RT, FULL, TMA>(g, s, q, rows, width, links, above ? 1u : ef_target, seed, lane);
         seed = false;
         if (!above || s.status != kQueryOk) break;
         cull<EF_T>(s, lane, /*next_big=*/(cur - 1 == target_layer));
@@ -965,7 +1028,8 @@ __device__ __forceinline__ void descend(const GraphView& g, WarpState& s, const 
 // ---------------------------------------------------------------------------------------------------------
 struct TablePool {
     uint32_t* slot_masks;     // [word]: bit i set = slot i taken
-    int32_t fixed_word;       // >= 0: claim from this word (the retry pool); < 0: from word %smid
+    int32_t fixed_word;       // >= 0: claim from this word (the retry pool); < 0: from word %smid  (%smid < %nsmid, which may exceed
+                              // the number of ENABLED SMs: the pool is sized by %nsmid)
     uint32_t word_base;       // subtracted from the word when the table index is formed (retry pool: its word; else 0)
     uint32_t slots_per_word;  // <= 32
     uint32_t* vis_tables;     // (word * slots_per_word + slot) * kWarpsPerCta + warp  ->  vis_stride words

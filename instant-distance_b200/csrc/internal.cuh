@@ -69,10 +69,12 @@ struct LaunchWindow {
 struct DeviceCtx {
     int device = 0;
     int num_sms = 148;
+    int sm_ids = 148;                      // %nsmid: SM ids are < sm_ids, which can exceed the number of enabled SMs (148 of 160 on B200)
     int slots_per_sm = kSearchCtasPerSm;   // CTA slots per SM (IDB_CTAS_PER_SM)
     std::mutex mu;                         // held while tables are (re)allocated and while a launch that uses them is enqueued
-    uint32_t* slot_masks = nullptr;        // num_sms words + 1 (the retry pool)
-    uint32_t n_tables = 0;                 // num_sms * slots_per_sm * kSearchWarps
+    uint32_t* slot_masks = nullptr;        // sm_ids words + 1 (the retry pool)
+    uint32_t n_tables = 0;                 // sm_ids * slots_per_sm * kSearchWarps (only those of enabled SMs are ever touched)
+    uint32_t n_tables_live = 0;            // num_sms * slots_per_sm * kSearchWarps: how many can be in use at once
     // b16 tier: fixed stride per warp, a prefix of it in use per call
     uint32_t* b16_tables = nullptr;
     uint32_t b16_stride = 0;               // u32 words per warp

@@ -9,6 +9,11 @@ cudaError_t dispatch_search_ch1(const SearchArgs& a, int row_t, int ef_t, int gr
             case 2: return launch_search<1, 2, 4, 8, 6>(a, grid, st, win);
             case 3: return launch_search<1, 2, 4, 4, 8>(a, grid, st, win);
             case 4: return launch_search<1, 2, 4, 16, 3>(a, grid, st, win);
+            // EXPERIMENT (profiles/r02_experiment_tma_ring.md): rows via cp.async.bulk into a shared-memory ring, no register staging
+            case 5: if (!a.g.bf16) return launch_search<1, 2, 4, 16, 4, RowF32, false, true>(a, grid, st, win); break;
+            case 6: if (!a.g.bf16) return launch_search<1, 2, 4, 8, 5, RowF32, false, true>(a, grid, st, win); break;
+            case 7: if (!a.g.bf16) return launch_search<1, 2, 4, 8, 6, RowF32, false, true>(a, grid, st, win); break;
+            case 8: if (!a.g.bf16) return launch_search<1, 2, 4, 32, 2, RowF32, false, true>(a, grid, st, win); break;
             default: break;
         }
     }

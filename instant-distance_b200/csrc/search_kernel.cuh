@@ -51,7 +51,7 @@ __device__ __forceinline__ void bind_tables(WarpState& s, const TablePool& tp, u
     s.tie_cap = tp.tie_cap;
 }
 
-template <int CH, int ROW_T, int EF_T, int B, int OCC, class RT = RowF32, bool FULL = false>
+template <int CH, int ROW_T, int EF_T, int B, int OCC, class RT = RowF32, bool FULL = false, bool TMA = false>
 __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_claim[2];
@@ -65,6 +65,18 @@ __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchAr
     const uint32_t table0 = cta_tables_acquire(a.pool, s_claim, kSearchWarps);
     bind_tables(s, a.pool, table0 + warp, a.gslots, a.gshift, a.vis_mode, a.b16_cap_ids);
     vis_clear_small(s.vis, lane);  // the big tables are handed over clean by their previous holder
+    if constexpr (TMA) {  // EXPERIMENT: per-warp ring of B rows + its mbarrier behind the traversal state
+        unsigned char* rb = smem_raw + (size_t)kSearchWarps * WarpSmem<EF_T>::kBytes;
+        s.mbar = reinterpret_cast<uint64_t*>(rb) + warp;
+        s.ring = reinterpret_cast<char*>(rb + 64 + (size_t)warp * B * a.g.nchunks * 16);
+        s.mbar_phase = 0;
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(s.mbar)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+    }
 
     for (;;) {
         unsigned long long w = 0;
@@ -77,7 +89,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchAr
         long_q_bind<EF_T>(q, smem_raw, a.g.nchunks, warp, kSearchWarps);
         q_from_f32<CH>(q, a.queries + qi * a.g.nchunks, a.g.nchunks, lane);
 
-        descend<CH, ROW_T, EF_T, B, false, RT, FULL>(a.g, s, q, 0u, a.ef, lane, a.counters ? a.counters + qi * 4 : nullptr);
+        descend<CH, ROW_T, EF_T, B, false, RT, FULL, TMA>(a.g, s, q, 0u, a.ef, lane, a.counters ? a.counters + qi * 4 : nullptr);
 
         const bool ok = s.status == kQueryOk;
         const uint64_t* near = (s.near_base + s.cur * s.near_len);
@@ -125,10 +137,11 @@ static cudaError_t launch_with_window(Kern kern, int grid, int block, int smem, 
     return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
-template <int CH, int ROW_T, int EF_T, int B, int OCC = kSearchCtasPerSm, class RT = RowF32, bool FULL = false>
+template <int CH, int ROW_T, int EF_T, int B, int OCC = kSearchCtasPerSm, class RT = RowF32, bool FULL = false, bool TMA = false>
 static cudaError_t launch_search(const SearchArgs& a, int grid, cudaStream_t stream, const LaunchWindow& win) {
-    const int smem = (WarpSmem<EF_T>::kBytes + (CH == 0 ? (int)long_q_bytes(a.g.nchunks) : 0)) * kSearchWarps;
-    auto kern = search_kernel<CH, ROW_T, EF_T, B, OCC, RT, FULL>;
+    const int smem = (WarpSmem<EF_T>::kBytes + (CH == 0 ? (int)long_q_bytes(a.g.nchunks) : 0)) * kSearchWarps +
+                     (TMA ? 64 + kSearchWarps * B * (int)a.g.nchunks * 16 : 0);
+    auto kern = search_kernel<CH, ROW_T, EF_T, B, OCC, RT, FULL, TMA>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     return launch_with_window(kern, grid, kSearchWarps * 32, smem, stream, win, a);

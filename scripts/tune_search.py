@@ -30,15 +30,10 @@ import torch  # noqa: E402
 
 from instant_distance_b200 import _abi  # noqa: E402
 
-pts, gen = bench.make_workload(args)
-try:
-    p, zero, upper, how = bench.obtain_graph(args, pts, 0)
-except Exception as e:  # noqa: BLE001  (e.g. the GPU build failed: fall back to a smaller oracle-built graph)
-    print("graph via", args.graph, "failed:", e, file=sys.stderr)
-    args.graph, args.n = "oracle", min(args.n, 300_000)
-    pts, gen = bench.make_workload(args)
-    p, zero, upper, how = bench.obtain_graph(args, pts, 0)
-print(json.dumps({"graph": how, "n": args.n}), flush=True)
+gen = bench.generator(args.data)
+pts = gen(args.n, args.dim, 1)
+p, zero, upper, _ = bench.obtain_graph(pts, args.n, args.dim, args.data, 1, args.M, args.efc, args.ef, args.seed, 0, use_abi=True)
+print(json.dumps({"graph": bench.GRAPH_NOTE, "n": args.n, "data": args.data, "ef": args.ef}), flush=True)
 del pts
 qs = [torch.from_numpy(gen(args.batch, args.dim, 7000 + s)).cuda() for s in range(args.steps + 2)]
 k = 10
@@ -66,9 +61,12 @@ for cfg in args.configs.split(";"):
     if ref_ids is None:
         ref_ids = ids
     same = bool((ids == ref_ids).all())
-    byts = float(bench.algorithmic_bytes(ix.last_counters(args.batch), args.dim, args.M, k).sum())
+    cnt = ix.last_counters(args.batch)
+    byts = float(bench.algorithmic_bytes(cnt, args.dim, args.M, k).sum())
     r = {"config": cfg, "kernel_ms": float(np.mean(ms)), "min_ms": float(np.min(ms)), "GBps": byts / (np.mean(ms) / 1e3) / 1e9,
-         "qps": args.batch / (np.mean(ms) / 1e3), "same_ids": same}
+         "frac": byts / (np.mean(ms) / 1e3) / 1e9 / bench.measured_peaks()[0], "qps": args.batch / (np.mean(ms) / 1e3), "same_ids": same,
+         "failed_after_retry": ix.last_failures(0), "n_dist_zero_mean": float(cnt[:, 3].mean()), "n_dist_zero_p999": float(np.quantile(cnt[:, 3], 0.999)),
+         "n_dist_zero_max": int(cnt[:, 3].max()), "n_expand_zero_mean": float(cnt[:, 2].mean())}
     print(json.dumps(r), flush=True)
     results.append(r)
     ix.close()
