@@ -400,11 +400,13 @@ def leg_search(a, rank, local_rank, world, full=True):
         iso_ms.append(ms)
         alg_bytes.append(float(algorithmic_bytes(ix.last_counters(nq), a.dim, a.M, K).sum()))
     assert ix.last_failures(0) == 0
+    retried = ix.last_retried(0)
     alg = float(np.mean(alg_bytes))
     peak, peak_src = measured_peaks()
     k_ms = dev_ms / a.steps
     res = {
         "value": qps, "ms_per_step": dev_ms / a.steps, "recall_at_10": recall, "ef_search": ef, "gpu_launches": launches, "clocks": clocks,
+        "retried_per_launch": retried,
         "roofline": {"bound": "hbm", "achieved": alg / (k_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg / (k_ms / 1e3) / 1e9 / peak, "traffic": None, "kernel": "search_kernel (K1 search_layer)",
                      "kernel_ms": k_ms, "kernel_ms_note": "timed region / launches, two launches in flight (successive launches overlap at the batch boundary)",
@@ -517,7 +519,14 @@ def leg_sharded(a, rank, local_rank, world, full=True):
         box = [uid]
         dist.broadcast_object_list(box, src=0)
         uid = box[0]
-    comm = _abi.Comm(uid, rank, world, local_rank)
+    sys.stdout.flush()
+    saved = os.dup(1)  # NCCL prints its version banner on stdout when NCCL_DEBUG is set: keep stdout to the ONE JSON line
+    os.dup2(2, 1)
+    try:
+        comm = _abi.Comm(uid, rank, world, local_rank)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
     shards[0].set_profiling(True)
 
     total = a.warmup + a.steps

@@ -128,6 +128,10 @@ IDB_API uint32_t idb_index_num_lanes(void);
 IDB_API void* idb_index_lane_stream(idb_index* index, uint32_t lane);  /* cudaStream_t of that lane */
 /* Waits for the last call on `lane` and reports how many of its queries failed even in the retry pass (0 = all results valid). */
 IDB_API idb_status idb_last_search_failures(idb_index* index, uint32_t lane, uint32_t* out_failed);
+/* Diagnostics: how many queries of the last call on `lane` overflowed their per-warp visited table / tie list in the main pass and were
+ * re-run by the retry pass (their results are valid; a persistently non-zero figure costs throughput, and the library then switches the
+ * index to its larger, DRAM-resident visited flavour by itself). */
+IDB_API idb_status idb_last_search_retried(idb_index* index, uint32_t lane, uint32_t* out_retried);
 /* enabled = 0: this library never touches the device's persisting-L2 limit nor attaches access-policy windows on `device`. */
 IDB_API idb_status idb_device_set_persisting_l2(int32_t device, int32_t enabled);
 

@@ -295,7 +295,16 @@ void Lane::free_all() {
     cudaFree(keys_local); cudaFree(keys_all); cudaFree(q2); cudaFree(ids2);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (ev_ctrl) cudaEventDestroy(ev_ctrl);
+    if (h_ctrl) cudaFreeHost(h_ctrl);
     if (stream) cudaStreamDestroy(stream);
+}
+
+void Index::note_overflows(uint32_t ef, uint64_t n_work, uint32_t overflowed) {
+    if ((uint64_t)overflowed * 1000 > n_work) {
+        uint32_t cur = b16_demote_ef.load();
+        while (ef < cur && !b16_demote_ef.compare_exchange_weak(cur, ef)) {}
+    }
 }
 
 Lane& Index::pick_lane() {
@@ -313,7 +322,15 @@ Lane& Index::pick_lane() {
 }
 
 idb_status Index::ensure_lane_scratch(Lane& ln, uint64_t nq) {
-    if (!ln.ctrl) CUDA_TRY(cudaMalloc(&ln.ctrl, 64));
+    if (!ln.ctrl) {
+        CUDA_TRY(cudaMalloc(&ln.ctrl, 64));
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&ln.h_ctrl), 64, cudaHostAllocDefault));
+        CUDA_TRY(cudaEventCreateWithFlags(&ln.ev_ctrl, cudaEventDisableTiming));
+    }
+    if (ln.ctrl_pending && cudaEventQuery(ln.ev_ctrl) == cudaSuccess) {  // the previous call's tally has arrived
+        if (ln.ctrl_b16) note_overflows(ln.ctrl_ef, ln.ctrl_nq, ln.h_ctrl[4]);
+        ln.ctrl_pending = false;
+    }
     CUDA_TRY(ensure(ln.status, ln.status_cap, nq));
     CUDA_TRY(ensure(ln.fail_list, ln.fail_cap, nq));
     CUDA_TRY(ensure(ln.counters, ln.counters_cap, nq * 4));
@@ -331,16 +348,22 @@ idb_status Index::ensure_lane_scratch(Lane& ln, uint64_t nq) {
 idb_status Index::select_visited_tier(uint32_t ef, SearchArgs& a, LaunchWindow& win) {
     DeviceCtx& c = *ctx;
     const uint32_t efx = std::max<uint32_t>(ef, 16u);
-    uint32_t b16_bytes = (uint32_t)std::min<uint64_t>(((uint64_t)2 * M * efx * 4 + 511) / 512 * 512, (uint64_t)c.b16_stride * 4);
-    if (b16_bytes_override) b16_bytes = std::min<uint32_t>(std::max<uint32_t>(b16_bytes_override / 32 * 32, 64u), c.b16_stride * 4);
-    const uint32_t nb = b16_bytes / 32;
+    // 2.5 u16 slots per id the traversal can possibly insert (2M per expansion, ~ef expansions): typical load 1/3, queries handed to the
+    // retry pass beyond 11/16 (profiles/r02_call4_tune_*: 1M x 128 sift, ef 100 / 128 / 200 visit at most 6.0k / 7.2k / 10.7k ids)
+    uint32_t b16_bytes = (uint32_t)std::min<uint64_t>(((uint64_t)2 * M * efx * 5 + 511) / 512 * 512, (uint64_t)c.b16_stride * 4);
+    if (b16_bytes_override) b16_bytes = std::min<uint32_t>(std::max<uint32_t>(b16_bytes_override / 32 * 32, 512u), c.b16_stride * 4);
+    const uint32_t nb = (b16_bytes - kB16Stash * 4) / 32;  // buckets, then the stash
     const bool b16_exact = rows_distinct && (n + 32767) / 32768 <= nb;
+    // worth it only if a typical traversal (~0.8 * 2M * ef ids) stays below the hand-over point, and this index has not been seen to
+    // overflow at this ef
+    const bool b16_roomy = (uint64_t)2 * M * efx * 4 <= (uint64_t)nb * 11 * 5 && ef < b16_demote_ef.load();
     int tier = vis_tier;
-    if (tier < 0 || (tier == 2 && !b16_exact)) tier = b16_exact ? 2 : -1;
+    if (tier == 2 && !b16_exact) tier = -1;
+    if (tier < 0) tier = (b16_exact && (b16_roomy || b16_bytes_override)) ? 2 : -1;
     win = LaunchWindow();
     if (tier == 2) {
         a.pool = c.main_pool(true);
-        a.gslots = nb * 8;
+        a.gslots = nb * 8 + kB16Stash;
         a.gshift = 0;
         a.vis_mode = kVisB16;
         a.b16_cap_ids = nb * 11;  // <= 11 of 16 slots on average; fuller tables hand the query to the retry pass
@@ -415,7 +438,7 @@ idb_status Index::enqueue_search(Lane& ln, const float* d_queries_padded, uint64
     ln.last_launches = 2;  // K1 + the (normally idle) retry pass
 
     // Retry pass (device-side, unconditional, normally a no-op): queries whose visited table overflowed are re-run
-    // by a few warps with 2^21-slot hash sets.  n_work is read from fail_count on the device.
+    // by a few warps with 2^18-slot hash sets.  n_work is read from fail_count on the device.
     SearchArgs r = a;
     r.work_list = ln.fail_list;
     r.n_work_dev = a.fail_count;
@@ -425,9 +448,16 @@ idb_status Index::enqueue_search(Lane& ln, const float* d_queries_padded, uint64
     r.fail_list = nullptr;       // failures of the retry pass are only counted (and visible in status[])
     r.pool = ctx->retry_pool();
     r.gslots = kRetrySlots;
-    r.gshift = 32 - 21;
+    r.gshift = 32 - 18;
     r.vis_mode = kVisHash;
+    static_assert(kRetrySlots == 1u << 18, "gshift above");
     CUDA_TRY(dispatch_search(r, ch, row_t, ef_t, kRetryCtas, ln.stream, LaunchWindow()));
+    CUDA_TRY(cudaMemcpyAsync(ln.h_ctrl, ln.ctrl, 64, cudaMemcpyDeviceToHost, ln.stream));
+    CUDA_TRY(cudaEventRecord(ln.ev_ctrl, ln.stream));
+    ln.ctrl_pending = true;
+    ln.ctrl_b16 = a.vis_mode == kVisB16;
+    ln.ctrl_ef = ef;
+    ln.ctrl_nq = nq;
     ln.last_nq = nq;
     return IDB_OK;
 }
@@ -751,6 +781,8 @@ idb_status idb_search_batch_f32(idb_index* index, const float* queries, uint64_t
     uint32_t ctrl[16];
     CUDA_TRY(cudaMemcpyAsync(ctrl, ln.ctrl, 64, cudaMemcpyDeviceToHost, ln.stream));
     CUDA_TRY(cudaStreamSynchronize(ln.stream));
+    if (ln.ctrl_b16) ix->note_overflows(ln.ctrl_ef, nq, ctrl[4]);
+    ln.ctrl_pending = false;
     if (ctrl[12] != 0)  // failures that survived the retry pass
         return fail(IDB_ERR_CAPACITY, "%u of %llu queries overflowed an internal per-query structure (visited table / tie list)",
                     ctrl[12], (unsigned long long)nq);
@@ -770,6 +802,22 @@ idb_status idb_last_search_failures(idb_index* index, uint32_t lane, uint32_t* o
     CUDA_TRY(cudaMemcpyAsync(ctrl, ln.ctrl, 64, cudaMemcpyDeviceToHost, ln.stream));
     CUDA_TRY(cudaStreamSynchronize(ln.stream));
     *out_failed = ctrl[12];
+    return IDB_OK;
+}
+
+idb_status idb_last_search_retried(idb_index* index, uint32_t lane, uint32_t* out_retried) {
+    if (!index || !out_retried) return fail(IDB_ERR_INVALID_ARG, "null argument");
+    Index* ix = reinterpret_cast<Index*>(index);
+    if (lane >= (uint32_t)kLanes) return fail(IDB_ERR_INVALID_ARG, "lane %u out of range", lane);
+    Lane& ln = ix->lanes[lane];
+    std::lock_guard<std::mutex> lk(ln.mu);
+    *out_retried = 0;
+    if (!ln.ctrl || ln.last_nq == 0) return IDB_OK;
+    CUDA_TRY(cudaSetDevice(ix->device));
+    uint32_t ctrl[16];
+    CUDA_TRY(cudaMemcpyAsync(ctrl, ln.ctrl, 64, cudaMemcpyDeviceToHost, ln.stream));
+    CUDA_TRY(cudaStreamSynchronize(ln.stream));
+    *out_retried = ctrl[4];
     return IDB_OK;
 }
 

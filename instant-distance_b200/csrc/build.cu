@@ -147,7 +147,7 @@ struct BuildScratch {
     // [0..8) KA work counter, [8..16) relink work counter, [16..20) n_seg, [20..24) KA fail count, [24..32) KA-retry work counter
     // (all reset per batch); [32..36) inserts that failed even in the retry pass (never reset)
     unsigned char* ctrl = nullptr;
-    uint32_t* h_fail = nullptr;     // pinned
+    uint32_t* h_fail = nullptr;     // pinned, 2 words: [0] failed even in the retry pass, [1] KA overflows of the last batch
     ~BuildScratch() {
         cudaFree(cand_keys); cudaFree(cand_cnt); cudaFree(pairs); cudaFree(sorted); cudaFree(seg_start); cudaFree(status);
         cudaFree(fail_list); cudaFree(cub_tmp); cudaFree(ctrl);
@@ -237,7 +237,7 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
     CUDA_TRY(cudaMalloc(&bs.seg_start, (size_t)max_batch * cap * 4));
     CUDA_TRY(cudaMalloc(&bs.status, (size_t)max_batch * 4));
     CUDA_TRY(cudaMalloc(&bs.fail_list, (size_t)max_batch * 4));
-    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&bs.h_fail), 4, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&bs.h_fail), 8, cudaHostAllocDefault));
     CUDA_TRY(cudaMalloc(&bs.ctrl, 64));
     CUDA_TRY(cudaMemsetAsync(bs.ctrl, 0, 64, st));
     CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, bs.cub_bytes, bs.pairs, bs.sorted, (int)(max_batch * cap), 0, 64, st));
@@ -282,7 +282,7 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
             a.layer = layer;
             a.n_pairs_cap = (uint32_t)(b * cap);
             CUDA_TRY(cudaMemsetAsync(bs.ctrl, 0, 32, st));
-            // KA: descent of every insert, then (device-side, normally a no-op) a retry pass with 2^21-slot hash sets and 64k-entry
+            // KA: descent of every insert, then (device-side, normally a no-op) a retry pass with 2^18-slot hash sets and 64k-entry
             // tie lists for the inserts whose per-warp structures overflowed (e.g. inside a cluster of thousands of duplicate vectors)
             BuildLaunch l;
             l.op = kOpInsertSearch;
@@ -312,13 +312,15 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
                 r.work_counter = reinterpret_cast<unsigned long long*>(bs.ctrl + 24);
                 r.pool = ix->ctx->retry_pool();
                 r.gslots = kRetrySlots;
-                r.gshift = 32 - 21;
+                r.gshift = 32 - 18;
                 r.vis_mode = kVisHash;
                 lr.grid = kRetryCtas;
                 lr.win = LaunchWindow();
                 CUDA_TRY(build_dispatch_any(ch, r, lr, st));
             }
             CUDA_TRY(cudaMemcpyAsync(bs.h_fail, bs.ctrl + 32, 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(bs.h_fail + 1, bs.ctrl + 20, 4, cudaMemcpyDeviceToHost, st));
+            const bool ka_b16 = a.vis_mode == kVisB16;
             // K2: neighbour selection for the new nodes, own rows, link requests
             if (p.heuristic) {
                 l.op = kOpSelectNew;
@@ -344,6 +346,7 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
             if (*bs.h_fail)
                 return fail(IDB_ERR_CAPACITY, "%u inserts overflowed an internal per-insert structure (visited table / tie list) in the batch ending at %llu",
                             *bs.h_fail, (unsigned long long)g0);
+            if (ka_b16) ix->note_overflows(efc, b, bs.h_fail[1]);  // too many b16 overflows: later batches use the atomic flavours
             if (p.progress) p.progress(g0, n, p.progress_user);  // set_position (core:519-525)
         }
         if (layer != 0) {  // lib.rs:323-328

@@ -223,7 +223,7 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
 struct VisitedSet {
     uint32_t* small;   // shared
     uint32_t* big;     // global
-    uint32_t gslots;   // words in use: hash slots (power of two) / bitmap words / 8 * buckets (b16)
+    uint32_t gslots;   // words in use: hash slots (power of two) / bitmap words / 8 * buckets + kB16Stash (b16)
     uint32_t gshift;   // hash flavour: 32 - log2(gslots)
     uint32_t count;
     bool use_big;
@@ -231,6 +231,7 @@ struct VisitedSet {
     uint32_t nb;       // b16 flavour: buckets in use
     float nb_inv;      // 1 / nb
     uint32_t cap_ids;  // b16 flavour: ids the table may hold before the query is handed to the retry pass
+    uint32_t stash_cnt;  // b16 flavour: ids in the stash (warp-uniform)
     uint32_t* hist;    // shared, 256 words = 1024 one-byte tallies, one per bucket: slots handed out since the snapshots of the current row
                        // were taken (b16 flavour; aliases WarpState::ckey, dead in that phase) — hence at most 1024 buckets per table
 };
@@ -274,13 +275,16 @@ __device__ __forceinline__ uint32_t vis_bitmap_fetch_clear(uint32_t* tab, uint32
 
 // ---- b16 bucket set --------------------------------------------------------------------------------------
 // Invariants (no deletions, slots of a bucket are filled in order 0..15):
-//   * an id lives in its home bucket if that bucket had a free slot when the id was inserted, else (flagged "displaced") in the
-//     next bucket; so "not in the home bucket, and the home bucket still has a free slot" proves absence with ONE 32-byte read;
+//   * an id lives in its home bucket if that bucket had a free slot when the id was inserted; else, flagged "displaced", in its
+//     alternate bucket (home + a step derived from the tag: double hashing, still invertible); else, as a full PointId, in a
+//     64-entry stash behind the buckets.  So "not in the home bucket, and the home bucket still has a free slot" proves absence
+//     with ONE 32-byte read, and only ids whose home bucket is full ever look further;
 //   * the warp owns the table: concurrent inserts only ever come from lanes of this warp handling the same adjacency row, and
 //     those are arbitrated in registers (match_any on the home bucket) plus an exact per-bucket tally in shared memory (one byte
 //     per bucket) for row entries that live in different registers, so inserts are plain stores and nobody waits for them.
 //   * PointIds within one adjacency row are distinct (true for every graph this library or the reference builds; adopted graphs
 //     are checked at upload and fall back to the atomic flavours if a row repeats an id).
+constexpr uint32_t kB16Stash = 64;  // u32 words behind the buckets: ids whose home and alternate buckets were both full
 struct Bucket8 { uint4 lo, hi; };
 struct B16 { uint32_t home, tag; };
 __device__ __forceinline__ Bucket8 bucket_load(const uint32_t* tab, uint32_t b) {
@@ -337,27 +341,44 @@ __device__ __forceinline__ uint32_t b16_tally_add(VisitedSet& v, uint32_t b, uin
     const uint32_t sh = 8u * (b & 3u);
     return (atomicAdd(&v.hist[b >> 2], n << sh) >> sh) & 0xFFu;
 }
-// Exact insert by ONE lane on fresh data (the others wait): 1 inserted, 0 already there, 2 no room within two buckets.
-__device__ __forceinline__ uint32_t b16_insert_slow(VisitedSet& v, B16 t) {
-    uint32_t b = t.home, val = t.tag;
-    for (int step = 0;; ++step) {
+// Exact insert by ONE lane on fresh data (the others wait): 1 inserted, 0 already there, 2 no room (home, alternate and stash full).
+// *stashed is set when the id went to the stash (the caller bumps the warp-uniform stash count).
+__device__ __forceinline__ uint32_t b16_insert_slow(VisitedSet& v, B16 t, uint32_t pid, bool* stashed) {
+    {
+        const Bucket8 k = bucket_load(v.big, t.home);
+        if (b16_has(k, t.tag)) return 0u;
+        const uint32_t cnt = b16_count(k);
+        if (cnt < 16u) {
+            b16_store(v.big, t.home, cnt, t.tag);
+            b16_tally_add(v, t.home, 1u);  // row entries in other registers hold an older snapshot of this bucket
+            return 1u;
+        }
+    }
+    if (t.tag != 0x7FFFu) {  // (0x8000 | 0x7FFF is the EMPTY pattern: such an id cannot be stored displaced)
+        uint32_t b = t.home + 1u + ((t.tag * 0x85EBCA6Bu) >> 12) % (v.nb - 1u);  // step in [1, nb): a function of the tag alone
+        if (b >= v.nb) b -= v.nb;
+        const uint32_t val = 0x8000u | t.tag;
         const Bucket8 k = bucket_load(v.big, b);
         if (b16_has(k, val)) return 0u;
         const uint32_t cnt = b16_count(k);
         if (cnt < 16u) {
             b16_store(v.big, b, cnt, val);
-            b16_tally_add(v, b, 1u);  // row entries in other registers hold an older snapshot of this bucket
+            b16_tally_add(v, b, 1u);
             return 1u;
         }
-        if (step == 1 || t.tag == 0x7FFFu) return 2u;  // 0x8000 | 0x7FFF is the EMPTY pattern: cannot be stored displaced
-        b = b + 1 == v.nb ? 0u : b + 1;
-        val = 0x8000u | t.tag;
     }
+    uint32_t* stash = v.big + (size_t)v.nb * 8;
+    for (uint32_t i = 0; i < v.stash_cnt; ++i)
+        if (__ldcg(stash + i) == pid) return 0u;
+    if (v.stash_cnt >= kB16Stash) return 2u;
+    __stcg(stash + v.stash_cnt, pid);
+    *stashed = true;
+    return 1u;
 }
 // Visited::insert (types.rs:32-40) for one id per lane, given the snapshot `bk` of its home bucket (loaded by the caller so that
 // the snapshots of a whole row are in flight together).  Warp-uniform call.  v.hist entries of the homes involved must have been
 // zeroed since the snapshots were taken (b16_tally_reset).  Returns true iff the id was not in the set; *ovf on overflow.
-__device__ __forceinline__ bool b16_commit(VisitedSet& v, B16 tg, const Bucket8& bk, bool want, int lane, bool* ovf) {
+__device__ __forceinline__ bool b16_commit(VisitedSet& v, B16 tg, uint32_t pid, const Bucket8& bk, bool want, int lane, bool* ovf) {
     bool isnew = false, slow = false;
     uint32_t cnt = 0;
     if (want && !b16_has(bk, tg.tag)) {
@@ -380,11 +401,13 @@ __device__ __forceinline__ bool b16_commit(VisitedSet& v, B16 tg, const Bucket8&
         __syncwarp();  // orders the stores above / of the previous turn before this turn's loads
         const int src = __ffs(sm) - 1;
         sm &= sm - 1;
+        bool stashed = false;
         if (lane == src) {
-            const uint32_t r = b16_insert_slow(v, tg);
+            const uint32_t r = b16_insert_slow(v, tg, pid, &stashed);
             isnew = r == 1u;
             if (r == 2u) *ovf = true;
         }
+        v.stash_cnt += __shfl_sync(kFullMask, stashed ? 1u : 0u, src);
     }
     __syncwarp();
     return isnew;
@@ -399,7 +422,7 @@ __device__ __forceinline__ bool vis_insert_big_any(VisitedSet& v, uint32_t pid, 
         bk.lo = bk.hi = make_uint4(0u, 0u, 0u, 0u);
         if (want) { bk = bucket_load(v.big, tg.home); b16_tally_reset(v, tg); }
         __syncwarp();
-        return b16_commit(v, tg, bk, want, lane, ovf);
+        return b16_commit(v, tg, pid, bk, want, lane, ovf);
     }
     if (!want) return false;
     if (v.mode == kVisBitmap) return (vis_bitmap_fetch_clear(v.big, pid) >> (pid & 31)) & 1u;
@@ -422,6 +445,7 @@ __device__ __forceinline__ void vis_clear_big(VisitedSet& v, int lane) {
 __device__ __forceinline__ void vis_clear(VisitedSet& v, int lane, bool next_big) {
     if (v.use_big) vis_clear_big(v, lane); else vis_clear_small(v, lane);
     v.count = 0;
+    v.stash_cnt = 0;
     v.use_big = next_big;
 }
 __device__ __forceinline__ void vis_migrate_to_big(VisitedSet& v, int lane) {
@@ -476,7 +500,7 @@ __device__ __forceinline__ bool vis_insert(VisitedSet& v, uint32_t pid, bool wan
     return vis_settle(v, pid, want, vis_probe(v, pid, want, lane));
 }
 // Make room for `incoming` more ids.  Returns false if the big table would get too full (the query is aborted with
-// kQueryVisitedOverflow and re-run by the retry pass with a 2^21-slot hash set).
+// kQueryVisitedOverflow and re-run by the retry pass with a 2^18-slot hash set).
 __device__ __forceinline__ bool vis_reserve(VisitedSet& v, uint32_t incoming, int lane) {
     if (!v.use_big && v.count + incoming > kSmallVisSlots / 2) vis_migrate_to_big(v, lane);
     if (v.use_big && v.mode == kVisHash && v.count + incoming > (v.gslots / 4) * 3) return false;
@@ -836,7 +860,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
                 bool ovf = false;
 #pragma unroll
                 for (int t = 0; t < ROW_T; ++t) {
-                    const bool fresh = b16_commit(s.vis, tg[t], bk[t], (uint32_t)(lane + 32 * t) < count, lane, &ovf);
+                    const bool fresh = b16_commit(s.vis, tg[t], ent[t], bk[t], (uint32_t)(lane + 32 * t) < count, lane, &ovf);
                     const uint32_t m = __ballot_sync(kFullMask, fresh);
                     if (fresh) s.cpid[n_new + __popc(m & lt_mask)] = ent[t];
                     n_new += __popc(m);

@@ -13,11 +13,17 @@
 
 namespace idb {
 
-constexpr int kSearchWarps = 4;        // warps (= live queries) per CTA
-constexpr int kSearchCtasPerSm = 4;    // resident CTAs per SM -> 16 live queries per SM, <= 128 registers per thread
-constexpr int kMaxCtasPerSm = 8;       // upper bound for IDB_CTAS_PER_SM
-constexpr int kRetryCtas = 8;          // CTA slots of the (normally idle) overflow-retry pool -> 32 warps
-constexpr uint32_t kRetrySlots = 1u << 21;
+// Warps (= live queries / inserts) per CTA of the traversal kernels.  A CTA's resources are only handed to the next launch when ALL its
+// warps have finished their last query, so fewer warps per CTA means the next batch moves in sooner at a batch boundary.
+#ifndef IDB_WPC
+#define IDB_WPC 4
+#endif
+constexpr int kSearchWarps = IDB_WPC;
+constexpr int kSearchCtasPerSm = 16 / IDB_WPC;  // resident CTAs per SM -> 16 live queries per SM, <= 128 registers per thread
+constexpr int kMaxCtasPerSm = 32 / IDB_WPC;     // upper bound for IDB_CTAS_PER_SM
+constexpr int kRetryCtas = 32 / IDB_WPC;        // CTA slots of the (normally idle) overflow-retry pool -> 32 warps
+constexpr int occ_for_warps(int warps_per_sm) { return warps_per_sm / IDB_WPC; }
+constexpr uint32_t kRetrySlots = 1u << 18;  // hash slots per retry warp: 196k ids at 3/4 load (2M * ef <= 131k for M <= 64, ef <= 1024)
 constexpr int kLanes = 4;              // submission lanes per index (own stream + per-call control state)
 
 extern thread_local char g_err[512];
@@ -117,6 +123,13 @@ struct Lane {
     float* q2 = nullptr;          size_t q2_cap = 0;
     uint32_t* ids2 = nullptr;     size_t ids2_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // asynchronous read-back of the control block of the lane's last call (how many queries overflowed the b16 tables)
+    uint32_t* h_ctrl = nullptr;      // pinned, 16 words
+    cudaEvent_t ev_ctrl = nullptr;
+    bool ctrl_pending = false;
+    bool ctrl_b16 = false;
+    uint32_t ctrl_ef = 0;
+    uint64_t ctrl_nq = 0;
     uint64_t last_nq = 0;
     uint32_t last_launches = 0;
     void free_all();
@@ -151,6 +164,11 @@ struct Index {
     uint32_t b16_bytes_override = 0; // IDB_B16_BYTES (tests / sweeps): exact b16 table bytes per warp in use
     int vis_tier = -1;            // IDB_VIS_TIER: -1 auto (b16 when exact for this n, else bitmap / hash), 0 hash, 1 bitmap, 2 b16
     int variant = 0;              // IDB_VARIANT: alternative (rows in flight, CTAs/SM) instantiations of K1
+    // Adaptive: when more than 1 in 1000 traversals of a call overflowed the b16 tables (data whose traversals visit more ids than
+    // the tables were sized for), later calls with that ef or a larger one use the DRAM-resident atomic flavours instead of paying
+    // for the retry pass.  Results are identical either way.
+    std::atomic<uint32_t> b16_demote_ef{0xFFFFFFFFu};
+    void note_overflows(uint32_t ef, uint64_t n_work, uint32_t overflowed);
     bool profiling = false;
 
     ~Index();

@@ -5,15 +5,15 @@ cudaError_t dispatch_search_ch1(const SearchArgs& a, int row_t, int ef_t, int gr
     // tuning variants of the headline shape (ROW_T=2, EF_T=4): rows in flight per lane x resident CTAs per SM
     if (a.variant && row_t <= 2 && ef_t <= 4) {
         switch (a.variant) {
-            case 1: return launch_search<1, 2, 4, 8, 5>(a, grid, st, win);
-            case 2: return launch_search<1, 2, 4, 8, 6>(a, grid, st, win);
-            case 3: return launch_search<1, 2, 4, 4, 8>(a, grid, st, win);
-            case 4: return launch_search<1, 2, 4, 16, 3>(a, grid, st, win);
+            case 1: return launch_search<1, 2, 4, 8, occ_for_warps(20)>(a, grid, st, win);
+            case 2: return launch_search<1, 2, 4, 8, occ_for_warps(24)>(a, grid, st, win);
+            case 3: return launch_search<1, 2, 4, 4, occ_for_warps(32)>(a, grid, st, win);
+            case 4: return launch_search<1, 2, 4, 16, occ_for_warps(12)>(a, grid, st, win);
             // EXPERIMENT (profiles/r02_experiment_tma_ring.md): rows via cp.async.bulk into a shared-memory ring, no register staging
-            case 5: if (!a.g.bf16) return launch_search<1, 2, 4, 16, 4, RowF32, false, true>(a, grid, st, win); break;
-            case 6: if (!a.g.bf16) return launch_search<1, 2, 4, 8, 5, RowF32, false, true>(a, grid, st, win); break;
-            case 7: if (!a.g.bf16) return launch_search<1, 2, 4, 8, 6, RowF32, false, true>(a, grid, st, win); break;
-            case 8: if (!a.g.bf16) return launch_search<1, 2, 4, 32, 2, RowF32, false, true>(a, grid, st, win); break;
+            case 5: if (!a.g.bf16) return launch_search<1, 2, 4, 16, occ_for_warps(16), RowF32, false, true>(a, grid, st, win); break;
+            case 6: if (!a.g.bf16) return launch_search<1, 2, 4, 8, occ_for_warps(20), RowF32, false, true>(a, grid, st, win); break;
+            case 7: if (!a.g.bf16) return launch_search<1, 2, 4, 8, occ_for_warps(24), RowF32, false, true>(a, grid, st, win); break;
+            case 8: if (!a.g.bf16) return launch_search<1, 2, 4, 32, occ_for_warps(8), RowF32, false, true>(a, grid, st, win); break;
             default: break;
         }
     }

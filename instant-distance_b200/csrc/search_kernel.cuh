@@ -42,9 +42,10 @@ __device__ __forceinline__ void bind_tables(WarpState& s, const TablePool& tp, u
     s.vis.gslots = gslots;
     s.vis.gshift = gshift;
     s.vis.mode = mode;
-    s.vis.nb = gslots >> 3;
-    s.vis.nb_inv = 1.0f / (float)(gslots >> 3);
+    s.vis.nb = mode == kVisB16 ? (gslots - kB16Stash) >> 3 : 1u;
+    s.vis.nb_inv = 1.0f / (float)s.vis.nb;
     s.vis.cap_ids = cap_ids;
+    s.vis.stash_cnt = 0;
     s.vis.count = 0;
     s.vis.use_big = false;
     s.ties = tp.tie_tables + (size_t)table * tp.tie_cap;

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-LIB_PATH = os.path.join(_PKG, "lib", "libinstant_distance_b200.so")
+LIB_PATH = os.environ.get("IDB_LIB_PATH") or os.path.join(_PKG, "lib", "libinstant_distance_b200.so")  # (IDB_LIB_PATH: A/B builds)
 
 INVALID = 0xFFFFFFFF
 
@@ -17,7 +17,7 @@ OK, ERR_INVALID_ARG, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_IO, ERR_FORMAT, ERR_CAPACI
 
 SYMBOLS = [
     "idb_params_default", "idb_build_f32", "idb_index_from_graph_f32", "idb_index_from_graph_bf16", "idb_search_batch_f32",
-    "idb_search_batch_device", "idb_search_batch_device_lane", "idb_last_search_counters", "idb_last_search_failures",
+    "idb_search_batch_device", "idb_search_batch_device_lane", "idb_last_search_counters", "idb_last_search_failures", "idb_last_search_retried",
     "idb_index_num_lanes", "idb_index_lane_stream", "idb_device_set_persisting_l2", "idb_index_info", "idb_index_export_points",
     "idb_index_export_zero", "idb_index_export_upper", "idb_index_save", "idb_index_load", "idb_index_set_profiling", "idb_index_last_kernel_ms", "idb_debug_gather_bench", "idb_debug_gather_mix_bench",
     "idb_index_stream", "idb_index_sync", "idb_index_free",
@@ -71,6 +71,7 @@ def lib():
     L.idb_search_batch_device_lane.argtypes = [vp, C.c_uint32, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp]
     L.idb_last_search_counters.argtypes = [vp, C.c_uint64, u64p]
     L.idb_last_search_failures.argtypes = [vp, C.c_uint32, u32p]
+    L.idb_last_search_retried.argtypes = [vp, C.c_uint32, u32p]
     L.idb_index_num_lanes.restype = C.c_uint32
     L.idb_index_lane_stream.argtypes = [vp, C.c_uint32]
     L.idb_index_lane_stream.restype = vp
@@ -234,6 +235,11 @@ class Index:
 
     def lane_stream(self, lane):
         return lib().idb_index_lane_stream(self._h, lane)
+
+    def last_retried(self, lane=0):
+        out = C.c_uint32()
+        check(lib().idb_last_search_retried(self._h, lane, C.byref(out)))
+        return int(out.value)
 
     def last_failures(self, lane=0):
         out = C.c_uint32()

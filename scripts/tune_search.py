@@ -65,7 +65,7 @@ for cfg in args.configs.split(";"):
     byts = float(bench.algorithmic_bytes(cnt, args.dim, args.M, k).sum())
     r = {"config": cfg, "kernel_ms": float(np.mean(ms)), "min_ms": float(np.min(ms)), "GBps": byts / (np.mean(ms) / 1e3) / 1e9,
          "frac": byts / (np.mean(ms) / 1e3) / 1e9 / bench.measured_peaks()[0], "qps": args.batch / (np.mean(ms) / 1e3), "same_ids": same,
-         "failed_after_retry": ix.last_failures(0), "n_dist_zero_mean": float(cnt[:, 3].mean()), "n_dist_zero_p999": float(np.quantile(cnt[:, 3], 0.999)),
+         "retried": ix.last_retried(0), "failed_after_retry": ix.last_failures(0), "n_dist_zero_mean": float(cnt[:, 3].mean()), "n_dist_zero_p999": float(np.quantile(cnt[:, 3], 0.999)),
          "n_dist_zero_max": int(cnt[:, 3].max()), "n_expand_zero_mean": float(cnt[:, 2].mean())}
     print(json.dumps(r), flush=True)
     results.append(r)

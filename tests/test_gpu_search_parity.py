@@ -206,7 +206,7 @@ def test_concurrent_callers_share_one_index(abi, oracle):
 
 def test_visited_overflow_goes_through_the_retry_pass(abi, oracle, monkeypatch):
     """A per-warp visited table that is too small aborts the query (kQueryVisitedOverflow); the device-side retry pass
-    re-runs it with a 2^21-slot table.  Results must still be the oracle's."""
+    re-runs it with a 2^18-slot table.  Results must still be the oracle's."""
     pts = datagen.uniform(20_000, 16, 13)
     ix, _ = oracle.build(pts, seed=3, threads=8)
     g = ix.export()
@@ -238,7 +238,7 @@ def test_search_parity_every_visited_flavour(abi, oracle, monkeypatch, flavour):
 
 
 def test_bucket_set_overflow_goes_through_the_retry_pass(abi, oracle, monkeypatch):
-    """A bucket set that is too small for the ids a query visits hands the query to the retry pass (hash set, 2^21 slots)."""
+    """A bucket set that is too small for the ids a query visits hands the query to the retry pass (hash set, 2^18 slots)."""
     pts = datagen.uniform(20_000, 16, 13)
     ix, _ = oracle.build(pts, seed=3, threads=8)
     g = ix.export()
