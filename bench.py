@@ -219,6 +219,7 @@ def obtain_graph(pts, n, dim, data, data_seed, M, efc, ef, seed, device, use_abi
         ix, ids = O.build(pts, M=M, ef_construction=efc, ef_search=ef, seed=seed, threads=host_threads())
         g = ix.export()
         zero, upper = g.zero, g.upper
+        GRAPH_HOW["by"] = "oracle (reference algorithm, threaded CPU build): no GPU was available to this arm"
         log("graph built by the oracle (CPU) — NOT the GPU build's graph")
     log(f"graph built in {time.time() - t:.1f}s (setup, untimed)")
     if not no_cache:
@@ -230,19 +231,20 @@ def obtain_graph(pts, n, dim, data, data_seed, M, efc, ef, seed, device, use_abi
 
 
 GRAPH_NOTE = "GPU Builder::build of this library (deterministic in the seed; untimed setup), searched by both arms"
+GRAPH_HOW = {"by": GRAPH_NOTE}  # replaced when a graph had to be built by the oracle on the CPU (no GPU on the box)
 
 
 def search_config(a, world, mode):
     par = "1 GPU" if world == 1 else f"replica x{world}, queries sharded, no collective"
     return {"workload": f"{a.n} x {a.dim} f32 {a.data}-shaped synthetic, M={a.M}, ef_construction={a.efc}, ef_search={a.ef}, "
                         f"batch={a.batch} queries/step, k={K}",
-            "graph": GRAPH_NOTE, "l2": "index >> 126 MB L2 and a fresh query batch per step (no flush needed)", "parallelism": par}
+            "graph": GRAPH_HOW["by"], "l2": "index >> 126 MB L2 and a fresh query batch per step (no flush needed)", "parallelism": par}
 
 
 def sharded_config(a, world):
     return {"workload": f"{N_SUB} x {a.shard_n} = {N_SUB * a.shard_n} x {a.dim} f32 sift-shaped synthetic in {N_SUB} sub-indexes by contiguous "
                         f"input range, M={a.M}, ef_construction={a.efc}, ef_search={a.ef}, batch={a.shard_batch} queries/step, k={K}",
-            "graph": GRAPH_NOTE, "l2": "every sub-index >> 126 MB L2 and a fresh query batch per step (no flush needed)",
+            "graph": GRAPH_HOW["by"], "l2": "every sub-index >> 126 MB L2 and a fresh query batch per step (no flush needed)",
             "parallelism": f"{N_SUB} sub-indexes over {world} GPU(s) ({N_SUB // world} per GPU), per-rank pre-merge + ONE ncclAllGather + merge"}
 
 

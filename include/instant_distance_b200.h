@@ -130,7 +130,7 @@ IDB_API void* idb_index_lane_stream(idb_index* index, uint32_t lane);  /* cudaSt
 IDB_API idb_status idb_last_search_failures(idb_index* index, uint32_t lane, uint32_t* out_failed);
 /* Diagnostics: how many queries of the last call on `lane` overflowed their per-warp visited table / tie list in the main pass and were
  * re-run by the retry pass (their results are valid; a persistently non-zero figure costs throughput, and the library then switches the
- * index to its larger, DRAM-resident visited flavour by itself). */
+ * index to its larger, DRAM-resident visited flavour by itself).  lane = 0xFFFFFFFF: the lane the last call on this index used. */
 IDB_API idb_status idb_last_search_retried(idb_index* index, uint32_t lane, uint32_t* out_retried);
 /* enabled = 0: this library never touches the device's persisting-L2 limit nor attaches access-policy windows on `device`. */
 IDB_API idb_status idb_device_set_persisting_l2(int32_t device, int32_t enabled);

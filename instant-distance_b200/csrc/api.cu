@@ -366,7 +366,7 @@ idb_status Index::select_visited_tier(uint32_t ef, SearchArgs& a, LaunchWindow& 
         a.gslots = nb * 8 + kB16Stash;
         a.gshift = 0;
         a.vis_mode = kVisB16;
-        a.b16_cap_ids = nb * 11;  // <= 11 of 16 slots on average; fuller tables hand the query to the retry pass
+        a.b16_cap_ids = nb * b16_cap_16ths;  // <= 11 of 16 slots on average; fuller tables hand the query to the retry pass
         idb_status st = c.reserve_l2((size_t)c.n_tables_live * b16_bytes);
         if (st != IDB_OK) return st;
         if (c.l2_reserved) {
@@ -452,12 +452,15 @@ idb_status Index::enqueue_search(Lane& ln, const float* d_queries_padded, uint64
     r.vis_mode = kVisHash;
     static_assert(kRetrySlots == 1u << 18, "gshift above");
     CUDA_TRY(dispatch_search(r, ch, row_t, ef_t, kRetryCtas, ln.stream, LaunchWindow()));
-    CUDA_TRY(cudaMemcpyAsync(ln.h_ctrl, ln.ctrl, 64, cudaMemcpyDeviceToHost, ln.stream));
-    CUDA_TRY(cudaEventRecord(ln.ev_ctrl, ln.stream));
-    ln.ctrl_pending = true;
-    ln.ctrl_b16 = a.vis_mode == kVisB16;
-    ln.ctrl_ef = ef;
-    ln.ctrl_nq = nq;
+    ln.last_b16 = a.vis_mode == kVisB16;
+    if (!ln.ctrl_pending) {  // sample this call's overflow tally (one read-back in flight per lane; evaluated by a later call)
+        CUDA_TRY(cudaMemcpyAsync(ln.h_ctrl, ln.ctrl, 64, cudaMemcpyDeviceToHost, ln.stream));
+        CUDA_TRY(cudaEventRecord(ln.ev_ctrl, ln.stream));
+        ln.ctrl_pending = true;
+        ln.ctrl_b16 = a.vis_mode == kVisB16;
+        ln.ctrl_ef = ef;
+        ln.ctrl_nq = nq;
+    }
     ln.last_nq = nq;
     return IDB_OK;
 }
@@ -543,6 +546,7 @@ idb_status Index::init_device(int dev) {
     if (const char* e = std::getenv("IDB_VIS_MULT")) vis_mult = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("IDB_VARIANT")) variant = std::atoi(e);
     if (const char* e = std::getenv("IDB_VIS_TIER")) vis_tier = std::atoi(e);
+    if (const char* e = std::getenv("IDB_B16_CAP")) b16_cap_16ths = (uint32_t)std::min(14, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("IDB_B16_BYTES")) b16_bytes_override = (uint32_t)std::max(64, std::atoi(e));
     if (const char* e = std::getenv("IDB_VIS_SLOTS")) vis_slots_override = next_pow2((uint64_t)std::max(64, std::atoi(e)));
     return IDB_OK;
@@ -781,8 +785,7 @@ idb_status idb_search_batch_f32(idb_index* index, const float* queries, uint64_t
     uint32_t ctrl[16];
     CUDA_TRY(cudaMemcpyAsync(ctrl, ln.ctrl, 64, cudaMemcpyDeviceToHost, ln.stream));
     CUDA_TRY(cudaStreamSynchronize(ln.stream));
-    if (ln.ctrl_b16) ix->note_overflows(ln.ctrl_ef, nq, ctrl[4]);
-    ln.ctrl_pending = false;
+    if (ln.last_b16) ix->note_overflows(ef, nq, ctrl[4]);
     if (ctrl[12] != 0)  // failures that survived the retry pass
         return fail(IDB_ERR_CAPACITY, "%u of %llu queries overflowed an internal per-query structure (visited table / tie list)",
                     ctrl[12], (unsigned long long)nq);
@@ -808,6 +811,7 @@ idb_status idb_last_search_failures(idb_index* index, uint32_t lane, uint32_t* o
 idb_status idb_last_search_retried(idb_index* index, uint32_t lane, uint32_t* out_retried) {
     if (!index || !out_retried) return fail(IDB_ERR_INVALID_ARG, "null argument");
     Index* ix = reinterpret_cast<Index*>(index);
+    if (lane == 0xFFFFFFFFu) lane = (uint32_t)ix->last_lane.load();  // the lane of the last call issued on this index
     if (lane >= (uint32_t)kLanes) return fail(IDB_ERR_INVALID_ARG, "lane %u out of range", lane);
     Lane& ln = ix->lanes[lane];
     std::lock_guard<std::mutex> lk(ln.mu);

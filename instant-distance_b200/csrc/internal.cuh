@@ -128,6 +128,7 @@ struct Lane {
     cudaEvent_t ev_ctrl = nullptr;
     bool ctrl_pending = false;
     bool ctrl_b16 = false;
+    bool last_b16 = false;           // the lane's last call used the b16 visited flavour
     uint32_t ctrl_ef = 0;
     uint64_t ctrl_nq = 0;
     uint64_t last_nq = 0;
@@ -162,6 +163,7 @@ struct Index {
     uint32_t vis_mult = 4;        // hash flavour: slots = next_pow2(vis_mult * 2M * ef): load <= ~0.15, probe chains ~1
     uint32_t vis_slots_override = 0; // IDB_VIS_SLOTS (tests): exact hash-table size, to force the overflow -> retry path
     uint32_t b16_bytes_override = 0; // IDB_B16_BYTES (tests / sweeps): exact b16 table bytes per warp in use
+    uint32_t b16_cap_16ths = 11;     // IDB_B16_CAP (tests): hand a query to the retry pass beyond this many sixteenths of the slots
     int vis_tier = -1;            // IDB_VIS_TIER: -1 auto (b16 when exact for this n, else bitmap / hash), 0 hash, 1 bitmap, 2 b16
     int variant = 0;              // IDB_VARIANT: alternative (rows in flight, CTAs/SM) instantiations of K1
     // Adaptive: when more than 1 in 1000 traversals of a call overflowed the b16 tables (data whose traversals visit more ids than

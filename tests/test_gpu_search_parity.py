@@ -285,3 +285,22 @@ def test_search_parity_oracle_built_200k_sift(abi, oracle):
     assert ix.num_layers == 8 and ix.layer_counts()[0] == 200_000
     _check(abi, oracle, g, ix, datagen.sift_shaped(5000, 128, 2), 100, k=100)
     _check(abi, oracle, g, ix, datagen.sift_shaped(2000, 128, 3), 200, k=10)
+
+
+def test_persistent_overflows_switch_the_index_to_the_atomic_flavour(abi, oracle, monkeypatch):
+    """Data whose traversals visit more ids than the b16 tables hold: every query is handed to the retry pass at first; the library
+    notices (sampled read-back of the overflow tally) and serves later calls from the DRAM-resident flavour.  Results never change."""
+    pts = datagen.uniform(20_000, 16, 13)
+    ix, _ = oracle.build(pts, seed=3, threads=8)
+    g = ix.export()
+    q = datagen.uniform(400, 16, 14)
+    want = ix.search(q, ef_search=100, k=10, counters=True)
+    monkeypatch.setenv("IDB_B16_CAP", "1")  # hand over beyond 1/16 of the slots: ~1000 ids at the default table size
+    gpu = abi.Index.from_graph(g.points, g.zero, g.upper, g.M)
+    retried = []
+    for _ in range(6):
+        got = gpu.search(q, ef_search=100, k=10)
+        assert (got[0] == want[0]).all() and got[1].tobytes() == want[1].tobytes() and (got[2] == want[2]).all()
+        assert (gpu.last_counters(len(q)) == want[3]).all()
+        retried.append(gpu.last_retried(0xFFFFFFFF))  # the lane the host call just used
+    assert retried[0] > 40 and retried[-1] == 0, retried
