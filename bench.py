@@ -803,10 +803,10 @@ def main():
     common = {"n_gpus": world, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "f32",
               "data": "synthetic"}
 
+    out = None
     if mode == "build":
         res = leg_build(a, local_rank)
-        if rank == 0:
-            print(json.dumps({**res, **common, "scaling": "weak"}), flush=True)
+        out = {**res, **common, "scaling": "weak"}
     elif mode == "headline":
         h = leg_search(a, rank, local_rank, world)
         line = {"metric": "batched QPS at recall@10>=0.95 (1M x 128 f32)", "value": h["value"], "unit": "queries/s", **common,
@@ -825,8 +825,7 @@ def main():
             line["uniform"] = {"what": "the same kernel on uniform-random 1M x 128 (north_star's wording): no neighbourhood structure, recall@10 stays far "
                                        "below 0.95 at any practical ef", "value": u["value"], "unit": "queries/s", "recall_at_10": u["recall_at_10"],
                                "ef_search": u["ef_search"], "k1_frac": u["roofline"]["frac"]}
-        if rank == 0:
-            print(json.dumps(line), flush=True)
+        out = line
     else:  # sharded
         s = leg_sharded(a, rank, local_rank, world)
         line = {"metric": "batched QPS, 10M x 128 f32 in 8 PointId-range sub-indexes (BASELINE configs[4])", "value": s["value"], "unit": "queries/s",
@@ -841,10 +840,11 @@ def main():
         line.update({"config": sharded_config(a, world), "recall_at_10": s["recall_at_10"], "ef_search": a.ef, "e2e": s.get("e2e"),
                      "gpu_launches": s["gpu_launches"], "roofline": s["roofline"], "merged_eq_protocol": s["merged_eq_protocol"],
                      "shard0_eq_oracle": s.get("shard0_eq_oracle"), "cpu_baseline": None, "clocks": s["clocks"]})
-        if rank == 0:
-            print(json.dumps(line), flush=True)
+        out = line
     if world > 1:
-        dist.destroy_process_group()
+        dist.destroy_process_group()  # (before the JSON line: NCCL's own log lines may share stdout)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":

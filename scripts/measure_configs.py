@@ -31,7 +31,7 @@ def run(name, gen, n, dim, M, efc, efs, nq, steps=5, storage="f32"):
     build_s = time.time() - t0
     p, zero, upper = ix.export_graph()
     rq = gen(1000, dim, 999)
-    truth = bench.brute_force_topk_torch(torch.from_numpy(p).cuda(), rq, 10)
+    truth = bench.brute_force_topk_torch(torch.from_numpy(p).cuda(), rq, 10)[0]
     torch.cuda.empty_cache()
     ix.set_profiling(True)
     del pts
@@ -50,12 +50,12 @@ def run(name, gen, n, dim, M, efc, efs, nq, steps=5, storage="f32"):
             t, _ = ix.last_kernel_ms()
             if s >= 2:
                 ms.append(t)
-        byts = float(bench.algorithmic_bytes(ix.last_counters(nq), dim if storage == "f32" else dim // 2, M, 10).sum())
+        byts = float(bench.algorithmic_bytes(ix.last_counters(nq), dim, M, 10, elem=4 if storage == "f32" else 2).sum())
         cnt = ix.last_counters(nq).mean(0).tolist()
         out["searches"].append({"ef_search": ef, "recall_at_10": rec, "kernel_ms": float(np.mean(ms)), "qps": nq / (np.mean(ms) / 1e3),
                                 "GBps": byts / (np.mean(ms) / 1e3) / 1e9, "frac_of_6572": byts / (np.mean(ms) / 1e3) / 1e9 / 6572.5,
-                                "counters_mean": cnt})
-        if rec >= 0.95 and name == "uniform" and ef > efs[0]:
+                                "counters_mean": cnt, "retried": ix.last_retried(0)})
+        if rec >= 0.95 and (name == "uniform" or name.startswith("config4")) and ef > efs[0]:
             break
     print(json.dumps(out), flush=True)
     ix.close()
@@ -70,7 +70,7 @@ for w in args.which.split(","):
     elif w == "config2":
         run("config2 2M x 300 M=24 efc=200", datagen.uniform, 2_000_000, 300, 24, 200, [100, 200], 10_000)
     elif w == "config4":
-        run("config4 5M x 768 bf16 ef=128 batch 64k", datagen.sift_shaped, 5_000_000, 768, 32, 100, [128], 65_536, steps=3, storage="bf16")
+        run("config4 5M x 768 bf16 ef=128 batch 64k", datagen.sift_shaped, 5_000_000, 768, 32, 100, [128, 160, 200, 256], 65_536, steps=3, storage="bf16")
     elif w == "config4s":
         run("config4 (1M subset) 1M x 768 bf16 ef=128 batch 64k", datagen.sift_shaped, 1_000_000, 768, 32, 100, [128], 65_536, steps=3, storage="bf16")
     elif w == "config2s":
