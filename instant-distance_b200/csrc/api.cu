@@ -321,6 +321,23 @@ Lane& Index::pick_lane() {
     return ln;
 }
 
+idb_status Index::attach_window(Lane& ln, const LaunchWindow& win) {
+    if (ln.win_base == win.base && ln.win_bytes == win.bytes) return IDB_OK;
+    cudaStreamAttrValue av;
+    std::memset(&av, 0, sizeof(av));
+    if (win.base && win.bytes) {
+        av.accessPolicyWindow.base_ptr = win.base;
+        av.accessPolicyWindow.num_bytes = win.bytes;
+        av.accessPolicyWindow.hitRatio = win.hit_ratio;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }
+    CUDA_TRY(cudaStreamSetAttribute(ln.stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    ln.win_base = win.base;
+    ln.win_bytes = win.bytes;
+    return IDB_OK;
+}
+
 idb_status Index::ensure_lane_scratch(Lane& ln, uint64_t nq) {
     if (!ln.ctrl) {
         CUDA_TRY(cudaMalloc(&ln.ctrl, 64));
@@ -431,6 +448,7 @@ idb_status Index::enqueue_search(Lane& ln, const float* d_queries_padded, uint64
     std::lock_guard<std::mutex> lk(ctx->mu);  // the tables this launch uses must not be regrown under it
     LaunchWindow win;
     st = select_visited_tier(ef, a, win);
+    if (st == IDB_OK) st = attach_window(ln, win);
     if (st != IDB_OK) return st;
     if (profiling) CUDA_TRY(cudaEventRecord(ln.ev0, ln.stream));
     CUDA_TRY(dispatch_search(a, ch, row_t, ef_t, grid, ln.stream, win));

@@ -249,6 +249,10 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
     bool stage = false;
     if (const char* e = std::getenv("IDB_BUILD_STAGE")) stage = std::atoi(e) != 0 && SelectSmem::bytes(cand_cap, M, ix->nchunks, true) <= 56 * 1024;
     const uint32_t k2_smem = (uint32_t)SelectSmem::bytes(cand_cap, M, ix->nchunks, stage);
+    // K2 / K2' are persistent grids of 2-warp CTAs.  ncu (profiles/r02_call10_k2p_ncu_raw.csv): 64 registers, issue-bound (68 % issue active
+    // with 16 warps per SM), so the grid asks for as many CTAs per SM as shared memory and registers allow, up to 16 (32 warps per SM).
+    int k2_ctas_per_sm = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, (200 * 1024) / std::max<uint32_t>(1, k2_smem * kBuildWarps)));
+    if (const char* e = std::getenv("IDB_BUILD_CTAS")) k2_ctas_per_sm = std::max(1, std::atoi(e));
 
     BuildArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -295,6 +299,7 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
                 std::lock_guard<std::mutex> lk(ix->ctx->mu);  // the pool's tables must not be regrown under these launches
                 SearchArgs tier;
                 idb_status ts = ix->select_visited_tier(efc, tier, l.win);
+                if (ts == IDB_OK) ts = ix->attach_window(ix->lanes[0], l.win);
                 if (ts != IDB_OK) return ts;
                 a.pool = tier.pool;
                 a.gslots = tier.gslots;
@@ -324,7 +329,7 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
             // K2: neighbour selection for the new nodes, own rows, link requests
             if (p.heuristic) {
                 l.op = kOpSelectNew;
-                l.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((b + kBuildWarps - 1) / kBuildWarps, (uint64_t)ix->num_sms * 8));
+                l.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((b + kBuildWarps - 1) / kBuildWarps, (uint64_t)ix->num_sms * k2_ctas_per_sm));
                 CUDA_TRY(build_dispatch_any(ch, a, l, st));
             } else {
                 select_simple_kernel<<<(unsigned)std::min<uint64_t>(b, 1024), 64, 0, st>>>(a);
@@ -338,7 +343,7 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
             CUDA_TRY(cudaGetLastError());
             // K2': re-prune every target row once
             l.op = p.heuristic ? kOpRelink : kOpRelinkSimple;
-            l.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((b * cap + kBuildWarps - 1) / kBuildWarps, (uint64_t)ix->num_sms * 8));
+            l.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((b * cap + kBuildWarps - 1) / kBuildWarps, (uint64_t)ix->num_sms * k2_ctas_per_sm));
             a.work_counter = reinterpret_cast<unsigned long long*>(bs.ctrl + 8);
             CUDA_TRY(build_dispatch_any(ch, a, l, st));
             g0 += b;

@@ -129,6 +129,8 @@ struct Lane {
     bool ctrl_pending = false;
     bool ctrl_b16 = false;
     bool last_b16 = false;           // the lane's last call used the b16 visited flavour
+    void* win_base = nullptr;        // access-policy window currently attached to the stream (see Index::attach_window)
+    size_t win_bytes = 0;
     uint32_t ctrl_ef = 0;
     uint64_t ctrl_nq = 0;
     uint64_t last_nq = 0;
@@ -184,6 +186,9 @@ struct Index {
     // Fills the visited-tier fields of `a` (pool, gslots, ...) for a traversal with this ef and returns the launch window.
     // Caller holds ctx->mu.
     idb_status select_visited_tier(uint32_t ef, SearchArgs& a, LaunchWindow& win);
+    // The persisting-L2 window on the b16 tables rides on every launch as a launch attribute; it is ALSO kept as a stream attribute,
+    // because profilers that replay a kernel (ncu) re-launch it without its launch attributes.
+    idb_status attach_window(Lane& ln, const LaunchWindow& win);
     idb_status ensure_lane_scratch(Lane& ln, uint64_t nq);
     idb_status enqueue_search(Lane& ln, const float* d_queries_padded, uint64_t nq, uint32_t ef, uint32_t k, uint32_t* d_ids,
                               float* d_dist, uint32_t* d_len, uint64_t* out_keys);
