@@ -689,6 +689,13 @@ def leg_build(a, local_rank):
         oi, _, _ = ox.search(rq[:200], ef_search=a.ef, k=K, threads=T)
         inv_s = np.empty(sub, dtype=np.int64)
         inv_s[o_ids] = np.arange(sub)
+        # the same subset built on the GPU: is the batched GPU graph as good as the reference algorithm's (recall within noise)?
+        gx, g_ids = _abi.Index.build(pts[:sub], M=a.M, ef_construction=a.efc, ef_search=a.ef, seed=a.seed, device=local_rank)
+        gi, _, _ = gx.search(rq[:200], ef_search=a.ef, k=K)
+        inv_g = np.empty(sub, dtype=np.int64)
+        inv_g[g_ids] = np.arange(sub)
+        res["recall_at_10_subset_gpu_graph"] = recall_at_k(inv_g[np.minimum(gi, sub - 1)], truth_s)
+        gx.close()
         res["cpu_baseline"] = {"value": sub / dt, "unit": "points/s", "cores": T, "kind": "port",
                                "sample": f"threaded build (lib.rs:313-318: top layer sequential, the rest parallel with per-row locks) of the first "
                                          f"{sub} points in {dt:.1f}s; HNSW insert cost grows ~log N, so the full-size rate is lower",

@@ -160,3 +160,17 @@ def test_progress_callback(abi):
     assert seen and all(t == 5000 for _, t in seen) and seen[-1][0] == 5000
     assert all(a[0] <= b[0] for a, b in zip(seen, seen[1:]))
     ix.close()
+
+
+def test_graph_tool_builds_the_same_graph_as_the_in_process_build(abi, tmp_path, monkeypatch):
+    """lib/idb_build_graph (plain C++ over the C ABI; bench.py's untimed graph-setup step) == Index.build in this process."""
+    import bench
+
+    monkeypatch.setenv("IDB_CACHE", str(tmp_path))
+    pts = datagen.sift_shaped(30_000, 64, 5)
+    ids_t, zero_t, upper_t, secs = bench.build_graph_with_tool(pts, 32, 100, 100, 77, 0)
+    ix, ids = abi.Index.build(pts, M=32, ef_construction=100, ef_search=100, seed=77)
+    _, zero, upper = ix.export_graph()
+    assert (ids_t == ids).all() and (zero_t == zero).all() and len(upper_t) == len(upper)
+    assert all((a == b).all() for a, b in zip(upper_t, upper)) and secs > 0
+    ix.close()
