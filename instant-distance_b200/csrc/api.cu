@@ -167,6 +167,8 @@ TablePool DeviceCtx::main_pool(bool b16) const {
     tp.slots_per_word = (uint32_t)slots_per_sm;
     tp.vis_tables = b16 ? b16_tables : big_tables;
     tp.vis_stride = b16 ? b16_stride : big_stride;
+    tp.vis_ext = b16 ? b16_ext : nullptr;
+    tp.ext_stride = b16 ? b16_stride : 0;
     tp.tie_tables = tie_tables;
     tp.tie_cap = kTieCap;
     return tp;
@@ -179,6 +181,8 @@ TablePool DeviceCtx::retry_pool() const {
     tp.slots_per_word = kRetryCtas;
     tp.vis_tables = retry_tables;
     tp.vis_stride = kRetrySlots;
+    tp.vis_ext = nullptr;
+    tp.ext_stride = 0;
     tp.tie_tables = retry_ties;
     tp.tie_cap = kRetryTieCap;
     return tp;
@@ -222,14 +226,19 @@ idb_status DeviceCtx::acquire(int device, DeviceCtx** out) {
     c->l2_allowed = g_l2_pref[device] >= 0;
     if (const char* e = std::getenv("IDB_L2_PERSIST")) c->l2_allowed = c->l2_allowed && std::atoi(e) != 0;
     // b16 tables: as many bytes per warp as keep ALL tables inside the persisting part of L2 (34 KB on B200: 79 MB / 2368 warps)
-    // (at most 32 KB = 1024 buckets: the per-row tally of the b16 flavour has one byte per bucket in 1 KB of shared memory)
+    // b16 tables: two segments of `b16_l2_bytes` per warp.  The first — as many bytes per warp as keep ALL live tables inside the
+    // persisting part of L2 (32 KB on B200: 79 MB / 2368 warps) and the pool inside one access-policy window — is what normal
+    // traversals use; the second serves large ef (up to 2040 buckets over both: the per-row tally has 2048 one-byte entries).
     size_t per = c->max_persist > 0 ? (size_t)c->max_persist / c->n_tables_live : (size_t)32 * 1024;
     per = std::min<size_t>(std::max<size_t>(per / 512 * 512, 8 * 1024), 32 * 1024);
+    c->b16_l2_bytes = (uint32_t)per;
     c->b16_stride = (uint32_t)(per / 4);
     CTX_TRY(cudaMalloc(&c->slot_masks, ((size_t)c->sm_ids + 1) * 4));
     CTX_TRY(cudaMemset(c->slot_masks, 0, ((size_t)c->sm_ids + 1) * 4));
     CTX_TRY(cudaMalloc(&c->b16_tables, (size_t)c->n_tables * per));
     CTX_TRY(cudaMemset(c->b16_tables, 0xFF, (size_t)c->n_tables * per));
+    CTX_TRY(cudaMalloc(&c->b16_ext, (size_t)c->n_tables * per));
+    CTX_TRY(cudaMemset(c->b16_ext, 0xFF, (size_t)c->n_tables * per));
     const size_t retry_words = (size_t)kRetryCtas * kSearchWarps * kRetrySlots;
     CTX_TRY(cudaMalloc(&c->retry_tables, retry_words * 4));
     CTX_TRY(cudaMemset(c->retry_tables, 0xFF, retry_words * 4));
@@ -260,6 +269,7 @@ DeviceCtx::~DeviceCtx() {
     }
     cudaFree(slot_masks);
     cudaFree(b16_tables);
+    cudaFree(b16_ext);
     cudaFree(big_tables);
     cudaFree(retry_tables);
     cudaFree(tie_tables);
@@ -300,10 +310,12 @@ void Lane::free_all() {
     if (stream) cudaStreamDestroy(stream);
 }
 
-void Index::note_overflows(uint32_t ef, uint64_t n_work, uint32_t overflowed) {
+void Index::note_overflows(uint32_t ef, uint64_t n_work, uint32_t overflowed, int level) {
+    if (level < 1 || level > 2) return;
     if ((uint64_t)overflowed * 1000 > n_work) {
-        uint32_t cur = b16_demote_ef.load();
-        while (ef < cur && !b16_demote_ef.compare_exchange_weak(cur, ef)) {}
+        std::atomic<uint32_t>& d = b16_demote_ef[level - 1];
+        uint32_t cur = d.load();
+        while (ef < cur && !d.compare_exchange_weak(cur, ef)) {}
     }
 }
 
@@ -345,7 +357,7 @@ idb_status Index::ensure_lane_scratch(Lane& ln, uint64_t nq) {
         CUDA_TRY(cudaEventCreateWithFlags(&ln.ev_ctrl, cudaEventDisableTiming));
     }
     if (ln.ctrl_pending && cudaEventQuery(ln.ev_ctrl) == cudaSuccess) {  // the previous call's tally has arrived
-        if (ln.ctrl_b16) note_overflows(ln.ctrl_ef, ln.ctrl_nq, ln.h_ctrl[4]);
+        note_overflows(ln.ctrl_ef, ln.ctrl_nq, ln.h_ctrl[4], ln.ctrl_b16);
         ln.ctrl_pending = false;
     }
     CUDA_TRY(ensure(ln.status, ln.status_cap, nq));
@@ -366,30 +378,48 @@ idb_status Index::select_visited_tier(uint32_t ef, SearchArgs& a, LaunchWindow& 
     DeviceCtx& c = *ctx;
     const uint32_t efx = std::max<uint32_t>(ef, 16u);
     // 2.5 u16 slots per id the traversal can possibly insert (2M per expansion, ~ef expansions): typical load 1/3, queries handed to the
-    // retry pass beyond 11/16 (profiles/r02_call4_tune_*: 1M x 128 sift, ef 100 / 128 / 200 visit at most 6.0k / 7.2k / 10.7k ids)
-    uint32_t b16_bytes = (uint32_t)std::min<uint64_t>(((uint64_t)2 * M * efx * 5 + 511) / 512 * 512, (uint64_t)c.b16_stride * 4);
-    if (b16_bytes_override) b16_bytes = std::min<uint32_t>(std::max<uint32_t>(b16_bytes_override / 32 * 32, 512u), c.b16_stride * 4);
-    const uint32_t nb = (b16_bytes - kB16Stash * 4) / 32;  // buckets, then the stash
+    // retry pass beyond 11/16 (profiles/r02_call4_tune_*: 1M x 128 sift, ef 100 / 128 / 200 visit at most 6.0k / 7.2k / 10.7k ids).
+    // Tables stay within the L2-resident 32 KB while 0.9 * 2M * ef ids fit below the hand-over point; larger ef uses up to 64 KB.
+    const uint64_t want_bytes = ((uint64_t)2 * M * efx * 5 + 511) / 512 * 512;
+    const uint32_t seg = c.b16_l2_bytes;                           // bytes per segment
+    const uint32_t nb_lo_max = (seg - kB16Stash * 4) / 32;         // the first segment also holds the stash
+    // Which flavour (profiles/r02_call13_tune_*):
+    //   1. b16 inside the L2-resident first segment while a typical traversal (~0.8 * 2M * ef ids) stays below its hand-over point
+    //      (M = 32: up to ef ~ 200) and this index has not been seen to overflow it at this ef;
+    //   2. b16 over both segments for BIG indexes only (n > 4M, where the bitmap would be > 512 KB per warp), same conditions;
+    //      at 1M points the half-DRAM-resident large table is no faster than the bitmap;
+    //   3. bitmap (n bits per warp) when that is no bigger than 2x the hash table, else the hash set.
+    auto cap_of = [&](uint32_t buckets) { return (uint64_t)buckets * b16_cap_16ths; };
+    const uint64_t typical = (uint64_t)2 * M * efx * 4 / 5;
+    int level = 0;
+    if (typical <= cap_of(nb_lo_max) && ef < b16_demote_ef[0].load()) level = 1;
+    else if (n > 4000000ull && typical <= cap_of(2040u) && ef < b16_demote_ef[1].load()) level = 2;
+    uint32_t b16_bytes = (uint32_t)std::min<uint64_t>(want_bytes, level == 2 ? 2ull * seg : seg);
+    if (b16_bytes_override) {
+        b16_bytes = std::min<uint32_t>(std::max<uint32_t>(b16_bytes_override / 32 * 32, 512u), 2 * seg);
+        if (ef < b16_demote_ef[0].load()) level = 1;
+    }
+    const uint32_t nb = std::min<uint32_t>((b16_bytes - kB16Stash * 4) / 32, 2040u);  // buckets over both segments
+    const uint32_t nb_lo = std::min(nb, nb_lo_max);
     const bool b16_exact = rows_distinct && (n + 32767) / 32768 <= nb;
-    // worth it only if a typical traversal (~0.8 * 2M * ef ids) stays below the hand-over point, and this index has not been seen to
-    // overflow at this ef
-    const bool b16_roomy = (uint64_t)2 * M * efx * 4 <= (uint64_t)nb * 11 * 5 && ef < b16_demote_ef.load();
     int tier = vis_tier;
     if (tier == 2 && !b16_exact) tier = -1;
-    if (tier < 0) tier = (b16_exact && (b16_roomy || b16_bytes_override)) ? 2 : -1;
+    if (tier < 0) tier = (b16_exact && level > 0) ? 2 : -1;
+    b16_level = tier == 2 ? (level > 0 ? level : 1) : 0;
     win = LaunchWindow();
     if (tier == 2) {
         a.pool = c.main_pool(true);
-        a.gslots = nb * 8 + kB16Stash;
+        a.gslots = nb_lo * 8 + kB16Stash;
+        a.b16_nb = nb;
         a.gshift = 0;
         a.vis_mode = kVisB16;
         a.b16_cap_ids = nb * b16_cap_16ths;  // <= 11 of 16 slots on average; fuller tables hand the query to the retry pass
-        idb_status st = c.reserve_l2((size_t)c.n_tables_live * b16_bytes);
+        idb_status st = c.reserve_l2((size_t)c.n_tables_live * std::min(b16_bytes, seg));
         if (st != IDB_OK) return st;
         if (c.l2_reserved) {
             win.base = c.b16_tables;
             win.bytes = std::min<size_t>((size_t)c.n_tables * c.b16_stride * 4, (size_t)c.max_window);
-            win.hit_ratio = 1.0f;  // only the first b16_bytes of every stride are ever touched
+            win.hit_ratio = 1.0f;  // the window covers the first segments only; of those only the bytes in use are ever touched
         }
         return IDB_OK;
     }
@@ -404,6 +434,7 @@ idb_status Index::select_visited_tier(uint32_t ef, SearchArgs& a, LaunchWindow& 
     a.gshift = 32 - (uint32_t)std::log2((double)want_slots);
     a.vis_mode = bitmap ? kVisBitmap : kVisHash;
     a.b16_cap_ids = 0;
+    a.b16_nb = 0;
     return IDB_OK;
 }
 
@@ -470,12 +501,12 @@ idb_status Index::enqueue_search(Lane& ln, const float* d_queries_padded, uint64
     r.vis_mode = kVisHash;
     static_assert(kRetrySlots == 1u << 18, "gshift above");
     CUDA_TRY(dispatch_search(r, ch, row_t, ef_t, kRetryCtas, ln.stream, LaunchWindow()));
-    ln.last_b16 = a.vis_mode == kVisB16;
+    ln.last_b16 = a.vis_mode == kVisB16 ? b16_level : 0;
     if (!ln.ctrl_pending) {  // sample this call's overflow tally (one read-back in flight per lane; evaluated by a later call)
         CUDA_TRY(cudaMemcpyAsync(ln.h_ctrl, ln.ctrl, 64, cudaMemcpyDeviceToHost, ln.stream));
         CUDA_TRY(cudaEventRecord(ln.ev_ctrl, ln.stream));
         ln.ctrl_pending = true;
-        ln.ctrl_b16 = a.vis_mode == kVisB16;
+        ln.ctrl_b16 = ln.last_b16;
         ln.ctrl_ef = ef;
         ln.ctrl_nq = nq;
     }
@@ -803,7 +834,7 @@ idb_status idb_search_batch_f32(idb_index* index, const float* queries, uint64_t
     uint32_t ctrl[16];
     CUDA_TRY(cudaMemcpyAsync(ctrl, ln.ctrl, 64, cudaMemcpyDeviceToHost, ln.stream));
     CUDA_TRY(cudaStreamSynchronize(ln.stream));
-    if (ln.last_b16) ix->note_overflows(ef, nq, ctrl[4]);
+    ix->note_overflows(ef, nq, ctrl[4], ln.last_b16);
     if (ctrl[12] != 0)  // failures that survived the retry pass
         return fail(IDB_ERR_CAPACITY, "%u of %llu queries overflowed an internal per-query structure (visited table / tie list)",
                     ctrl[12], (unsigned long long)nq);

@@ -306,6 +306,7 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
                 a.gshift = tier.gshift;
                 a.vis_mode = tier.vis_mode;
                 a.b16_cap_ids = tier.b16_cap_ids;
+                a.b16_nb = tier.b16_nb;
                 a.work_counter = reinterpret_cast<unsigned long long*>(bs.ctrl);
                 CUDA_TRY(build_dispatch_any(ch, a, l, st));
                 BuildArgs r = a;
@@ -325,7 +326,7 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
             }
             CUDA_TRY(cudaMemcpyAsync(bs.h_fail, bs.ctrl + 32, 4, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaMemcpyAsync(bs.h_fail + 1, bs.ctrl + 20, 4, cudaMemcpyDeviceToHost, st));
-            const bool ka_b16 = a.vis_mode == kVisB16;
+            const int ka_b16 = a.vis_mode == kVisB16 ? ix->b16_level : 0;
             // K2: neighbour selection for the new nodes, own rows, link requests
             if (p.heuristic) {
                 l.op = kOpSelectNew;
@@ -351,7 +352,7 @@ idb_status build_index(Index* ix, const float* rows, uint64_t n, uint32_t dim, c
             if (*bs.h_fail)
                 return fail(IDB_ERR_CAPACITY, "%u inserts overflowed an internal per-insert structure (visited table / tie list) in the batch ending at %llu",
                             *bs.h_fail, (unsigned long long)g0);
-            if (ka_b16) ix->note_overflows(efc, b, bs.h_fail[1]);  // too many b16 overflows: later batches use the atomic flavours
+            ix->note_overflows(efc, b, bs.h_fail[1], ka_b16);  // too many b16 overflows: later batches use a larger flavour
             if (p.progress) p.progress(g0, n, p.progress_user);  // set_position (core:519-525)
         }
         if (layer != 0) {  // lib.rs:323-328

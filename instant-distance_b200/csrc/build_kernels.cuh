@@ -43,6 +43,7 @@ struct BuildArgs {
     uint32_t gslots, gshift;
     uint32_t vis_mode;
     uint32_t b16_cap_ids;
+    uint32_t b16_nb;
     // relink
     const uint64_t* sorted_pairs;   // count*2M sorted ascending
     uint32_t n_pairs_cap;
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, kSearchCtasPerSm) insert_se
     WarpState s;
     WarpSmem<EF_T>::carve(s, smem_raw + (size_t)warp * WarpSmem<EF_T>::kBytes);
     const uint32_t table0 = cta_tables_acquire(a.pool, s_claim, kSearchWarps);
-    bind_tables(s, a.pool, table0 + warp, a.gslots, a.gshift, a.vis_mode, a.b16_cap_ids);
+    bind_tables(s, a.pool, table0 + warp, a.gslots, a.gshift, a.vis_mode, a.b16_cap_ids, a.b16_nb);
     vis_clear_small(s.vis, lane);
 
     for (;;) {

@@ -228,12 +228,15 @@ struct VisitedSet {
     uint32_t count;
     bool use_big;
     uint32_t mode;     // flavour of the big tier (VisMode).  A clean table is all ones (kInvalid) in every flavour
-    uint32_t nb;       // b16 flavour: buckets in use
+    uint32_t nb;       // b16 flavour: buckets in use: [0, nb_lo) in `big` (followed by the stash), [nb_lo, nb) in `big_hi`
+    uint32_t nb_lo;
+    uint32_t* big_hi;  // b16 flavour: second segment (outside the persisting-L2 window), pre-offset so that bucket b is at big_hi + 8 * b
     float nb_inv;      // 1 / nb
     uint32_t cap_ids;  // b16 flavour: ids the table may hold before the query is handed to the retry pass
     uint32_t stash_cnt;  // b16 flavour: ids in the stash (warp-uniform)
-    uint32_t* hist;    // shared, 256 words = 1024 one-byte tallies, one per bucket: slots handed out since the snapshots of the current row
-                       // were taken (b16 flavour; aliases WarpState::ckey, dead in that phase) — hence at most 1024 buckets per table
+    uint32_t* hist;    // shared, 512 words = 2048 one-byte tallies, one per bucket: slots handed out since the snapshots of the current row
+                       // were taken (b16 flavour).  Aliases `small`, which is idle (and clean) whenever the big tier is live and is
+                       // wiped again when the warp goes back to it — hence at most 2048 buckets (64 KB) per table
 };
 // Big-tier flavours, all exact:
 //   kVisHash    open addressing, one u32 slot per id, atomicCAS + linear probing (any n; the retry pass and the fallback)
@@ -287,15 +290,16 @@ __device__ __forceinline__ uint32_t vis_bitmap_fetch_clear(uint32_t* tab, uint32
 constexpr uint32_t kB16Stash = 64;  // u32 words behind the buckets: ids whose home and alternate buckets were both full
 struct Bucket8 { uint4 lo, hi; };
 struct B16 { uint32_t home, tag; };
-__device__ __forceinline__ Bucket8 bucket_load(const uint32_t* tab, uint32_t b) {
-    const uint4* p = reinterpret_cast<const uint4*>(tab + (size_t)b * 8);
+__device__ __forceinline__ uint32_t* bucket_ptr(const VisitedSet& v, uint32_t b) { return (b < v.nb_lo ? v.big : v.big_hi) + (size_t)b * 8; }
+__device__ __forceinline__ Bucket8 bucket_load(const VisitedSet& v, uint32_t b) {
+    const uint4* p = reinterpret_cast<const uint4*>(bucket_ptr(v, b));
     Bucket8 r;
     r.lo = __ldcg(p);      // L2 (never L1: other lanes of this warp write these sectors)
     r.hi = __ldcg(p + 1);
     return r;
 }
-__device__ __forceinline__ void b16_store(uint32_t* tab, uint32_t b, uint32_t pos, uint32_t val16) {
-    unsigned short* p = reinterpret_cast<unsigned short*>(tab) + ((size_t)b * 16 + pos);
+__device__ __forceinline__ void b16_store(const VisitedSet& v, uint32_t b, uint32_t pos, uint32_t val16) {
+    unsigned short* p = reinterpret_cast<unsigned short*>(bucket_ptr(v, b)) + pos;
     asm volatile("st.global.cg.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)val16) : "memory");
 }
 // (home bucket, 15-bit tag) of a PointId: tag = low 15 bits, home = (pid >> 15) + scramble(tag) mod nb.  Injective while
@@ -335,7 +339,7 @@ __device__ __forceinline__ uint32_t b16_count(const Bucket8& k) {
     }
     return 16u - __popc(m);
 }
-// Per-bucket tally (one byte per bucket, <= 1024 buckets): how many slots of bucket b were handed out since the current row's
+// Per-bucket tally (one byte per bucket, <= 2048 buckets): how many slots of bucket b were handed out since the current row's
 // snapshots were taken.  <= 128 per row (4 registers x 32 lanes), so a byte never carries into its neighbour.
 __device__ __forceinline__ uint32_t b16_tally_add(VisitedSet& v, uint32_t b, uint32_t n) {
     const uint32_t sh = 8u * (b & 3u);
@@ -345,11 +349,11 @@ __device__ __forceinline__ uint32_t b16_tally_add(VisitedSet& v, uint32_t b, uin
 // *stashed is set when the id went to the stash (the caller bumps the warp-uniform stash count).
 __device__ __forceinline__ uint32_t b16_insert_slow(VisitedSet& v, B16 t, uint32_t pid, bool* stashed) {
     {
-        const Bucket8 k = bucket_load(v.big, t.home);
+        const Bucket8 k = bucket_load(v, t.home);
         if (b16_has(k, t.tag)) return 0u;
         const uint32_t cnt = b16_count(k);
         if (cnt < 16u) {
-            b16_store(v.big, t.home, cnt, t.tag);
+            b16_store(v, t.home, cnt, t.tag);
             b16_tally_add(v, t.home, 1u);  // row entries in other registers hold an older snapshot of this bucket
             return 1u;
         }
@@ -358,16 +362,16 @@ __device__ __forceinline__ uint32_t b16_insert_slow(VisitedSet& v, B16 t, uint32
         uint32_t b = t.home + 1u + ((t.tag * 0x85EBCA6Bu) >> 12) % (v.nb - 1u);  // step in [1, nb): a function of the tag alone
         if (b >= v.nb) b -= v.nb;
         const uint32_t val = 0x8000u | t.tag;
-        const Bucket8 k = bucket_load(v.big, b);
+        const Bucket8 k = bucket_load(v, b);
         if (b16_has(k, val)) return 0u;
         const uint32_t cnt = b16_count(k);
         if (cnt < 16u) {
-            b16_store(v.big, b, cnt, val);
+            b16_store(v, b, cnt, val);
             b16_tally_add(v, b, 1u);
             return 1u;
         }
     }
-    uint32_t* stash = v.big + (size_t)v.nb * 8;
+    uint32_t* stash = v.big + (size_t)v.nb_lo * 8;
     for (uint32_t i = 0; i < v.stash_cnt; ++i)
         if (__ldcg(stash + i) == pid) return 0u;
     if (v.stash_cnt >= kB16Stash) return 2u;
@@ -393,7 +397,7 @@ __device__ __forceinline__ bool b16_commit(VisitedSet& v, B16 tg, uint32_t pid, 
     base = __shfl_sync(kFullMask, base, leader);
     if (isnew) {
         const uint32_t pos = cnt + base + __popc(peers & ((1u << lane) - 1u));
-        if (pos < 16u) b16_store(v.big, tg.home, pos, tg.tag);
+        if (pos < 16u) b16_store(v, tg.home, pos, tg.tag);
         else { isnew = false; slow = true; }
     }
     uint32_t sm = __ballot_sync(kFullMask, slow);
@@ -420,7 +424,7 @@ __device__ __forceinline__ bool vis_insert_big_any(VisitedSet& v, uint32_t pid, 
         const B16 tg = b16_of(v, pid);
         Bucket8 bk;
         bk.lo = bk.hi = make_uint4(0u, 0u, 0u, 0u);
-        if (want) { bk = bucket_load(v.big, tg.home); b16_tally_reset(v, tg); }
+        if (want) { bk = bucket_load(v, tg.home); b16_tally_reset(v, tg); }
         __syncwarp();
         return b16_commit(v, tg, pid, bk, want, lane, ovf);
     }
@@ -438,23 +442,33 @@ __device__ __forceinline__ void vis_clear_big(VisitedSet& v, int lane) {
     uint4* p = reinterpret_cast<uint4*>(v.big);
     const uint4 e = make_uint4(kInvalid, kInvalid, kInvalid, kInvalid);
     for (uint32_t i = lane; i < v.gslots / 4; i += 32) __stcg(p + i, e);
+    if (v.mode == kVisB16 && v.nb > v.nb_lo) {  // second segment of a large table
+        uint4* ph = reinterpret_cast<uint4*>(v.big_hi + (size_t)v.nb_lo * 8);
+        for (uint32_t i = lane; i < (v.nb - v.nb_lo) * 2; i += 32) __stcg(ph + i, e);
+    }
     __threadfence();  // plain stores must be ordered before later atomics from other lanes
     __syncwarp();
 }
 // Visited::clear (types.rs:48-58); `next_big` selects the tier for the layer about to be searched.
 __device__ __forceinline__ void vis_clear(VisitedSet& v, int lane, bool next_big) {
-    if (v.use_big) vis_clear_big(v, lane); else vis_clear_small(v, lane);
+    if (v.use_big) {
+        vis_clear_big(v, lane);
+        if (v.mode == kVisB16) vis_clear_small(v, lane);  // the b16 tally lives in the small tier's shared memory
+    } else {
+        vis_clear_small(v, lane);
+    }
     v.count = 0;
     v.stash_cnt = 0;
     v.use_big = next_big;
 }
 __device__ __forceinline__ void vis_migrate_to_big(VisitedSet& v, int lane) {
     bool ovf = false;  // (a few hundred ids into a table sized for thousands: cannot overflow)
-#pragma unroll 4
-    for (int i = 0; i < kSmallVisSlots / 32; ++i) {
-        const uint32_t x = v.small[lane + 32 * i];
-        vis_insert_big_any(v, x, x != kInvalid, lane, &ovf);
-    }
+    uint32_t x[kSmallVisSlots / 32];  // (read everything first: the b16 flavour keeps its per-row tally in this very memory)
+#pragma unroll
+    for (int i = 0; i < kSmallVisSlots / 32; ++i) x[i] = v.small[lane + 32 * i];
+    __syncwarp();
+#pragma unroll  // (fully unrolled so that x[] stays in registers; a cold path)
+    for (int i = 0; i < kSmallVisSlots / 32; ++i) vis_insert_big_any(v, x[i], x[i] != kInvalid, lane, &ovf);
     __syncwarp();
     vis_clear_small(v, lane);
     v.use_big = true;
@@ -854,7 +868,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
                 for (int t = 0; t < ROW_T; ++t) {
                     tg[t] = b16_of(s.vis, ent[t]);
                     bk[t].lo = bk[t].hi = make_uint4(0u, 0u, 0u, 0u);
-                    if ((uint32_t)(lane + 32 * t) < count) { bk[t] = bucket_load(s.vis.big, tg[t].home); b16_tally_reset(s.vis, tg[t]); }
+                    if ((uint32_t)(lane + 32 * t) < count) { bk[t] = bucket_load(s.vis, tg[t].home); b16_tally_reset(s.vis, tg[t]); }
                 }
                 __syncwarp();
                 bool ovf = false;
@@ -1058,6 +1072,8 @@ struct TablePool {
     uint32_t slots_per_word;  // <= 32
     uint32_t* vis_tables;     // (word * slots_per_word + slot) * kWarpsPerCta + warp  ->  vis_stride words
     uint32_t vis_stride;
+    uint32_t* vis_ext;        // b16 flavour: second segment of each table (ext_stride words), for tables beyond the first segment
+    uint32_t ext_stride;
     uint64_t* tie_tables;     // same index -> tie_cap keys
     uint32_t tie_cap;
 };

@@ -56,6 +56,7 @@ struct SearchArgs {
     uint32_t gslots, gshift;           // big visited tier: words in use per warp / hash flavour: 32 - log2(gslots)
     uint32_t vis_mode;                 // flavour of the big visited tier (hnsw_device.cuh VisMode)
     uint32_t b16_cap_ids;              // b16 flavour: ids per query before the retry pass takes over
+    uint32_t b16_nb;                   // b16 flavour: buckets in use over both segments
     uint64_t* out_keys;                // optional: nq x k packed (distance bits << 32 | id_map[pid]) for the sharded all-gather
     const uint32_t* id_map;            // optional: PointId -> caller's global row id
     int variant;                       // tuning variant of the kernel template (0 = default)
@@ -82,8 +83,10 @@ struct DeviceCtx {
     uint32_t n_tables = 0;                 // sm_ids * slots_per_sm * kSearchWarps (only those of enabled SMs are ever touched)
     uint32_t n_tables_live = 0;            // num_sms * slots_per_sm * kSearchWarps: how many can be in use at once
     // b16 tier: fixed stride per warp, a prefix of it in use per call
-    uint32_t* b16_tables = nullptr;
-    uint32_t b16_stride = 0;               // u32 words per warp
+    uint32_t* b16_tables = nullptr;        // first segment of every table: what normal traversals use, under the persisting-L2 window
+    uint32_t b16_stride = 0;               // u32 words per warp = b16_l2_bytes / 4
+    uint32_t b16_l2_bytes = 32 * 1024;     // bytes per warp that keep all live tables inside the persisting part of L2
+    uint32_t* b16_ext = nullptr;           // second segment (same size), used by traversals with a large ef; not under the window
     // atomic tiers (hash / bitmap): allocated on first use, regrown (device idle) when a call needs more
     uint32_t* big_tables = nullptr;
     uint32_t big_stride = 0;
@@ -127,8 +130,8 @@ struct Lane {
     uint32_t* h_ctrl = nullptr;      // pinned, 16 words
     cudaEvent_t ev_ctrl = nullptr;
     bool ctrl_pending = false;
-    bool ctrl_b16 = false;
-    bool last_b16 = false;           // the lane's last call used the b16 visited flavour
+    int ctrl_b16 = 0;
+    int last_b16 = 0;                // the lane's last call used the b16 visited flavour: 1 = first segment only, 2 = both segments
     void* win_base = nullptr;        // access-policy window currently attached to the stream (see Index::attach_window)
     size_t win_bytes = 0;
     uint32_t ctrl_ef = 0;
@@ -171,8 +174,9 @@ struct Index {
     // Adaptive: when more than 1 in 1000 traversals of a call overflowed the b16 tables (data whose traversals visit more ids than
     // the tables were sized for), later calls with that ef or a larger one use the DRAM-resident atomic flavours instead of paying
     // for the retry pass.  Results are identical either way.
-    std::atomic<uint32_t> b16_demote_ef{0xFFFFFFFFu};
-    void note_overflows(uint32_t ef, uint64_t n_work, uint32_t overflowed);
+    std::atomic<uint32_t> b16_demote_ef[2] = {{0xFFFFFFFFu}, {0xFFFFFFFFu}};  // [0] first-segment tables, [1] two-segment tables
+    int b16_level = 0;            // set by select_visited_tier (under ctx->mu): which b16 size the selected tier is (0 = not b16)
+    void note_overflows(uint32_t ef, uint64_t n_work, uint32_t overflowed, int level);
     bool profiling = false;
 
     ~Index();

@@ -23,7 +23,7 @@ struct WarpSmem {
         s.vis.small = reinterpret_cast<uint32_t*>(base + kNearBytes);
         s.cpid = s.vis.small + kSmallVisSlots;
         s.ckey = reinterpret_cast<uint64_t*>(s.cpid + 128);
-        s.vis.hist = reinterpret_cast<uint32_t*>(s.ckey);  // 256 words, only live between a row load and its distances
+        s.vis.hist = s.vis.small;  // the b16 tally borrows the small tier's 2 KB while the big tier is live (hnsw_device.cuh)
     }
 };
 // Long rows (CH == 0): the warps' query buffers follow the per-warp traversal state in dynamic shared memory.
@@ -36,13 +36,16 @@ __device__ __forceinline__ void long_q_bind(QVec<CH>& q, unsigned char* smem_raw
     }
 }
 // Point the warp at its claimed scratch tables.
+// b16 flavour: gslots = words of the first segment in use (8 * nb_lo + stash), b16_nb = buckets over both segments.
 __device__ __forceinline__ void bind_tables(WarpState& s, const TablePool& tp, uint32_t table, uint32_t gslots, uint32_t gshift,
-                                            uint32_t mode, uint32_t cap_ids) {
+                                            uint32_t mode, uint32_t cap_ids, uint32_t b16_nb) {
     s.vis.big = tp.vis_tables + (size_t)table * tp.vis_stride;
     s.vis.gslots = gslots;
     s.vis.gshift = gshift;
     s.vis.mode = mode;
-    s.vis.nb = mode == kVisB16 ? (gslots - kB16Stash) >> 3 : 1u;
+    s.vis.nb_lo = mode == kVisB16 ? (gslots - kB16Stash) >> 3 : 1u;
+    s.vis.nb = mode == kVisB16 ? b16_nb : 1u;
+    s.vis.big_hi = mode == kVisB16 && tp.vis_ext ? tp.vis_ext + (size_t)table * tp.ext_stride - (size_t)s.vis.nb_lo * 8 : s.vis.big;
     s.vis.nb_inv = 1.0f / (float)s.vis.nb;
     s.vis.cap_ids = cap_ids;
     s.vis.stash_cnt = 0;
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(kSearchWarps * 32, OCC) search_kernel(SearchAr
     WarpState s;
     WarpSmem<EF_T>::carve(s, smem_raw + (size_t)warp * WarpSmem<EF_T>::kBytes);
     const uint32_t table0 = cta_tables_acquire(a.pool, s_claim, kSearchWarps);
-    bind_tables(s, a.pool, table0 + warp, a.gslots, a.gshift, a.vis_mode, a.b16_cap_ids);
+    bind_tables(s, a.pool, table0 + warp, a.gslots, a.gshift, a.vis_mode, a.b16_cap_ids, a.b16_nb);
     vis_clear_small(s.vis, lane);  // the big tables are handed over clean by their previous holder
     if constexpr (TMA) {  // EXPERIMENT: per-warp ring of B rows + its mbarrier behind the traversal state
         unsigned char* rb = smem_raw + (size_t)kSearchWarps * WarpSmem<EF_T>::kBytes;

@@ -295,7 +295,7 @@ def test_persistent_overflows_switch_the_index_to_the_atomic_flavour(abi, oracle
     g = ix.export()
     q = datagen.uniform(400, 16, 14)
     want = ix.search(q, ef_search=100, k=10, counters=True)
-    monkeypatch.setenv("IDB_B16_CAP", "1")  # hand over beyond 1/16 of the slots: ~1000 ids at the default table size
+    monkeypatch.setenv("IDB_B16_BYTES", "4096")  # 120 buckets: handed over beyond 1320 ids, every query here visits > 2200
     gpu = abi.Index.from_graph(g.points, g.zero, g.upper, g.M)
     retried = []
     for _ in range(6):
