@@ -31,6 +31,10 @@ extern "C" {
     fn idb_search_batch_f32(ix: *mut IdbIndex, q: *const f32, nq: u64, ef: u32, k: u32, ids: *mut u32, dist: *mut f32, len: *mut u32) -> i32;
     fn idb_index_free(ix: *mut IdbIndex);
     fn idb_last_error() -> *const c_char;
+    // Batched / device-side / multi-GPU entry points (no counterpart in the reference; see include/instant_distance_b200.h):
+    //   idb_search_batch_device_lane, idb_index_lane_stream, idb_last_search_failures   — device buffers, 4 submission lanes per index
+    //   idb_comm_create, idb_index_set_id_map, idb_sharded_search_batch_f32_multi        — PointId-range shards + ONE all-gather
+    //   idb_device_set_persisting_l2                                                      — opt out of the persisting-L2 reservation
 }
 fn last_error() -> String {
     unsafe { CStr::from_ptr(idb_last_error()).to_string_lossy().into_owned() }
@@ -115,7 +119,7 @@ pub struct Search { nearest: Vec<(f32, PointId)> }
 /// lib.rs:193-199
 pub struct Hnsw { raw: *mut IdbIndex, points: Vec<F32Point>, ef_search: usize }
 unsafe impl Send for Hnsw {}
-unsafe impl Sync for Hnsw {} // calls serialise inside the library
+unsafe impl Sync for Hnsw {} // lib.rs:352-356: concurrent searches each take a submission lane inside the library and overlap on the device
 impl Drop for Hnsw {
     fn drop(&mut self) { unsafe { idb_index_free(self.raw) } }
 }

@@ -29,7 +29,7 @@ for cfg in configs.split(";"):
     ix.sync()
     bs = time.time() - t
     p, _, _ = ix.export_graph()
-    truth = bench.brute_force_topk_torch(torch.from_numpy(p).cuda(), rq, 10)
+    truth = bench.brute_force_topk_torch(torch.from_numpy(p).cuda(), rq, 10)[0]
     got, _, _ = ix.search(rq, ef_search=100, k=10)
     print(json.dumps({"config": cfg, "n": n, "build_s": round(bs, 2), "points_per_s": n / bs, "recall_at_10": bench.recall_at_k(got, truth)}), flush=True)
     ix.close()
