@@ -825,7 +825,8 @@ def main():
                                "recall_at_10": s["recall_at_10"], "merged_eq_protocol": s["merged_eq_protocol"], "gpu_launches": s["gpu_launches"],
                                "k1_frac": s["roofline"]["frac"]}
         line.update({"config": search_config(a, world, mode), "recall_at_10": h["recall_at_10"], "ef_search": h["ef_search"], "e2e": h.get("e2e"),
-                     "gpu_launches": h["gpu_launches"], "roofline": h["roofline"], "cpu_baseline": h.get("cpu_baseline"), "clocks": h["clocks"]})
+                     "gpu_launches": h["gpu_launches"], "retried_per_launch": h["retried_per_launch"], "roofline": h["roofline"],
+                     "cpu_baseline": h.get("cpu_baseline"), "clocks": h["clocks"]})
         if world == 1 and a.mode == "auto" and not a.skip_secondary:
             ua = argparse.Namespace(**{**vars(a), "data": "uniform", "steps": min(a.steps, 10)})
             u = leg_search(ua, rank, local_rank, world, full=False)

@@ -21,4 +21,18 @@ for (n, dim, M, ef, gen) in [(1500, 24, 32, 50, datagen.uniform), (800, 3, 32, 1
     o = ix.search(q, ef_search=ef, k=ef)
     assert (ids == o[0]).all() and dist.tobytes() == o[1].tobytes() and (lens == o[2]).all(), (n, dim, M, ef)
     gpu.close()
+# long rows (query in shared memory), a small GPU build (KA / K2 / K2' + the shared table pool), and a 3-shard world-of-one sharded search
+pts = datagen.uniform(400, 1100, 5)
+ix, _ = O.build(pts, seed=2)
+g = ix.export()
+gpu = _abi.Index.from_graph(g.points, g.zero, g.upper, g.M)
+q = datagen.uniform(16, 1100, 6)
+a, b = gpu.search(q, ef_search=20, k=20), ix.search(q, ef_search=20, k=20)
+assert (a[0] == b[0]).all() and a[1].tobytes() == b[1].tobytes()
+gpu.close()
+built, ids = _abi.Index.build(datagen.uniform(1500, 16, 7), seed=3, insert_batch=64)
+ref, _ = O.build(datagen.uniform(1500, 16, 7), seed=3)
+got = built.search(datagen.uniform(32, 16, 8), ef_search=50, k=10)
+assert (got[2] == 50).all()
+built.close()
 print("sanitize case ok")
