@@ -347,6 +347,7 @@ __device__ __forceinline__ uint32_t b16_tally_add(VisitedSet& v, uint32_t b, uin
 }
 // Exact insert by ONE lane on fresh data (the others wait): 1 inserted, 0 already there, 2 no room (home, alternate and stash full).
 // *stashed is set when the id went to the stash (the caller bumps the warp-uniform stash count).
+template <bool kTally>
 __device__ __forceinline__ uint32_t b16_insert_slow(VisitedSet& v, B16 t, uint32_t pid, bool* stashed) {
     {
         const Bucket8 k = bucket_load(v, t.home);
@@ -354,7 +355,7 @@ __device__ __forceinline__ uint32_t b16_insert_slow(VisitedSet& v, B16 t, uint32
         const uint32_t cnt = b16_count(k);
         if (cnt < 16u) {
             b16_store(v, t.home, cnt, t.tag);
-            b16_tally_add(v, t.home, 1u);  // row entries in other registers hold an older snapshot of this bucket
+            if (kTally) b16_tally_add(v, t.home, 1u);  // row entries in other registers hold an older snapshot of this bucket
             return 1u;
         }
     }
@@ -367,7 +368,7 @@ __device__ __forceinline__ uint32_t b16_insert_slow(VisitedSet& v, B16 t, uint32
         const uint32_t cnt = b16_count(k);
         if (cnt < 16u) {
             b16_store(v, b, cnt, val);
-            b16_tally_add(v, b, 1u);
+            if (kTally) b16_tally_add(v, b, 1u);
             return 1u;
         }
     }
@@ -380,8 +381,11 @@ __device__ __forceinline__ uint32_t b16_insert_slow(VisitedSet& v, B16 t, uint32
     return 1u;
 }
 // Visited::insert (types.rs:32-40) for one id per lane, given the snapshot `bk` of its home bucket (loaded by the caller so that
-// the snapshots of a whole row are in flight together).  Warp-uniform call.  v.hist entries of the homes involved must have been
-// zeroed since the snapshots were taken (b16_tally_reset).  Returns true iff the id was not in the set; *ovf on overflow.
+// the snapshots of a whole row are in flight together).  Warp-uniform call.  kTally: other registers of the same row hold snapshots
+// taken before this call's stores — the per-bucket tally (entries zeroed since the snapshots were taken, b16_tally_reset) keeps them
+// consistent; a caller whose snapshot is fresh and who inserts one register of ids at a time passes false and never touches the tally.
+// Returns true iff the id was not in the set; *ovf on overflow.
+template <bool kTally>
 __device__ __forceinline__ bool b16_commit(VisitedSet& v, B16 tg, uint32_t pid, const Bucket8& bk, bool want, int lane, bool* ovf) {
     bool isnew = false, slow = false;
     uint32_t cnt = 0;
@@ -393,8 +397,10 @@ __device__ __forceinline__ bool b16_commit(VisitedSet& v, B16 tg, uint32_t pid, 
     const uint32_t peers = __match_any_sync(kFullMask, isnew ? tg.home : (0x80000000u | (uint32_t)lane));
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
-    if (isnew && lane == leader) base = b16_tally_add(v, tg.home, (uint32_t)__popc(peers));
-    base = __shfl_sync(kFullMask, base, leader);
+    if (kTally) {
+        if (isnew && lane == leader) base = b16_tally_add(v, tg.home, (uint32_t)__popc(peers));
+        base = __shfl_sync(kFullMask, base, leader);
+    }
     if (isnew) {
         const uint32_t pos = cnt + base + __popc(peers & ((1u << lane) - 1u));
         if (pos < 16u) b16_store(v, tg.home, pos, tg.tag);
@@ -407,7 +413,7 @@ __device__ __forceinline__ bool b16_commit(VisitedSet& v, B16 tg, uint32_t pid, 
         sm &= sm - 1;
         bool stashed = false;
         if (lane == src) {
-            const uint32_t r = b16_insert_slow(v, tg, pid, &stashed);
+            const uint32_t r = b16_insert_slow<kTally>(v, tg, pid, &stashed);
             isnew = r == 1u;
             if (r == 2u) *ovf = true;
         }
@@ -424,9 +430,8 @@ __device__ __forceinline__ bool vis_insert_big_any(VisitedSet& v, uint32_t pid, 
         const B16 tg = b16_of(v, pid);
         Bucket8 bk;
         bk.lo = bk.hi = make_uint4(0u, 0u, 0u, 0u);
-        if (want) { bk = bucket_load(v, tg.home); b16_tally_reset(v, tg); }
-        __syncwarp();
-        return b16_commit(v, tg, pid, bk, want, lane, ovf);
+        if (want) bk = bucket_load(v, tg.home);  // a fresh snapshot, one register of ids: no tally needed
+        return b16_commit<false>(v, tg, pid, bk, want, lane, ovf);
     }
     if (!want) return false;
     if (v.mode == kVisBitmap) return (vis_bitmap_fetch_clear(v.big, pid) >> (pid & 31)) & 1u;
@@ -463,12 +468,11 @@ __device__ __forceinline__ void vis_clear(VisitedSet& v, int lane, bool next_big
 }
 __device__ __forceinline__ void vis_migrate_to_big(VisitedSet& v, int lane) {
     bool ovf = false;  // (a few hundred ids into a table sized for thousands: cannot overflow)
-    uint32_t x[kSmallVisSlots / 32];  // (read everything first: the b16 flavour keeps its per-row tally in this very memory)
-#pragma unroll
-    for (int i = 0; i < kSmallVisSlots / 32; ++i) x[i] = v.small[lane + 32 * i];
-    __syncwarp();
-#pragma unroll  // (fully unrolled so that x[] stays in registers; a cold path)
-    for (int i = 0; i < kSmallVisSlots / 32; ++i) vis_insert_big_any(v, x[i], x[i] != kInvalid, lane, &ovf);
+#pragma unroll 1  // (cold path; these single-register inserts never touch the b16 tally, which shares this memory)
+    for (int i = 0; i < kSmallVisSlots / 32; ++i) {
+        const uint32_t x = v.small[lane + 32 * i];
+        vis_insert_big_any(v, x, x != kInvalid, lane, &ovf);
+    }
     __syncwarp();
     vis_clear_small(v, lane);
     v.use_big = true;
@@ -874,7 +878,7 @@ __device__ __forceinline__ void search_layer(const GraphView& g, WarpState& s, c
                 bool ovf = false;
 #pragma unroll
                 for (int t = 0; t < ROW_T; ++t) {
-                    const bool fresh = b16_commit(s.vis, tg[t], ent[t], bk[t], (uint32_t)(lane + 32 * t) < count, lane, &ovf);
+                    const bool fresh = b16_commit<true>(s.vis, tg[t], ent[t], bk[t], (uint32_t)(lane + 32 * t) < count, lane, &ovf);
                     const uint32_t m = __ballot_sync(kFullMask, fresh);
                     if (fresh) s.cpid[n_new + __popc(m & lt_mask)] = ent[t];
                     n_new += __popc(m);
