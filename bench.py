@@ -394,12 +394,14 @@ def leg_search(a, rank, local_rank, world, full=True):
     sampler.stop()
     qps = world * nq * a.steps / (dev_ms / 1e3)
 
-    # isolated launches (one lane, event-bracketed per launch) + algorithmic bytes, on a second pass
+    # isolated launches (one lane, event-bracketed per launch, back to back), then the algorithmic bytes of the same batches
     iso_ms, alg_bytes = [], []
     for s in range(a.warmup, total):
         step(s, 0)
         ms, _ = ix.last_kernel_ms()
         iso_ms.append(ms)
+    for s in range(a.warmup, total):
+        step(s, 0)
         alg_bytes.append(float(algorithmic_bytes(ix.last_counters(nq), a.dim, a.M, K).sum()))
     assert ix.last_failures(0) == 0
     retried = ix.last_retried(0)
