@@ -12,11 +12,14 @@ A "step" = one pass of the hot path (Hnsw::search, lib.rs:352-383) over one batc
   issued alternately on two submission lanes, so consecutive launches overlap at the batch boundary); `e2e` = the same through
   idb_search_batch_f32 with pinned HOST buffers (H2D + D2H inside the timed region, two caller threads).  The line also carries
   `sharded` (BASELINE configs[4] on ONE GPU: 10M x 128 in 8 sub-indexes by contiguous input range, batch 100k — the denominator of
-  the 1 -> 8 GPU figure north_star asks for) and `uniform` (the same headline kernel on uniform-random data).
+  the 1 -> 8 GPU figure north_star asks for), `uniform` (the same headline kernel on uniform-random data) and `build` (BASELINE
+  configs[2]: GPU Builder::build of 2M x 300, M=24, ef_construction=200, then batch=10k search on that graph, next to the threaded CPU
+  build of the reference algorithm on a prefix).
 --gpus N > 1 (auto): BASELINE.json configs[4] — the same 8 sub-indexes spread over the N GPUs (8/N each), every query searched on
   every sub-index, per-rank pre-merge, ONE ncclAllGather of the per-rank top-k, merge kernel (idb_sharded_search_batch_*_multi).
-  `value` = queries/s of the whole job ("scaling": "strong"); `replicas` carries the configs[1] replica figure (queries sharded
-  over N copies of the 1M index, no collective) as a secondary field.
+  `value` = queries/s of the whole job ("scaling": "strong"); `one_gpu_same_layout` = the same 8 sub-indexes on ONE GPU, measured by
+  rank 0 in the same run (the denominator of the 1 -> N speed-up, SURVEY 8e; it is also `sharded` of the --gpus 1 line);
+  `replicas` carries the configs[1] replica figure (queries sharded over N copies of the 1M index, no collective) as a secondary field.
 --impl reference: the reference algorithm's CPU path (oracle/ restatement; the Rust crate cannot be built here) with all host
   threads, on the same config: N=1 -> configs[1]; N>1 -> configs[4] (rank 0 only; the other ranks exit).  It never loads the CUDA
   library: the graph both arms search is built in an untimed setup step by lib/idb_build_graph (a C++ program over the C ABI).
@@ -679,6 +682,33 @@ def leg_build(a, local_rank):
     res = {"metric": "GPU Builder::build throughput", "value": a.n / min(times), "unit": "points/s", "seconds": times,
            "recall_at_10_of_built_graph": recall, "ef_search": a.ef,
            "config": {"workload": f"{a.n} x {a.dim} f32 {a.data}-shaped synthetic, M={a.M}, ef_construction={a.efc}"}}
+    # batched search on the graph just built (configs[2]: "GPU Builder::build + batch=10k search"): ef_search raised until recall@10 >= 0.95
+    ef_s, rec_s = a.ef, recall
+    for cand in [128, 160, 200, 256, 320, 400, 512]:
+        if rec_s >= 0.95:
+            break
+        if cand <= ef_s:
+            continue
+        g_ids, _, _ = ix.search(rq, ef_search=cand, k=K)
+        ef_s, rec_s = cand, recall_at_k(inv[np.minimum(g_ids, a.n - 1)], truth)
+    nq = a.batch
+    dq = [torch.from_numpy(gen(nq, a.dim, 5000 + s)).cuda() for s in range(4)]
+    d_ids = torch.empty((nq, K), dtype=torch.int32, device="cuda")
+    d_dist = torch.empty((nq, K), dtype=torch.float32, device="cuda")
+    d_len = torch.empty((nq,), dtype=torch.int32, device="cuda")
+    ix.set_profiling(True)
+    k_ms, alg = [], []
+    for s in range(3 + 5):
+        ix.search_device(dq[s % 4].data_ptr(), nq, ef_s, K, d_ids.data_ptr(), d_dist.data_ptr(), d_len.data_ptr())
+        ms, _ = ix.last_kernel_ms()
+        if s >= 3:
+            k_ms.append(ms)
+            alg.append(float(algorithmic_bytes(ix.last_counters(nq), a.dim, a.M, K).sum()))
+    peak, _ = measured_peaks()
+    res["search"] = {"value": nq / (float(np.mean(k_ms)) / 1e3), "unit": "queries/s", "batch": nq, "ef_search": ef_s, "recall_at_10": rec_s,
+                     "kernel_ms": float(np.mean(k_ms)), "k1_frac": float(np.mean(alg)) / (float(np.mean(k_ms)) / 1e3) / 1e9 / peak,
+                     "what": "K1 launches of one 10k-query batch each (device-resident, isolated, 5 timed after 3 warm), on the graph built above"}
+    del dq, d_ids, d_dist, d_len
     if not a.skip_cpu_baseline:
         from oracle import oracle as O
 
@@ -807,7 +837,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=30))
     mode = a.mode if a.mode != "auto" else ("headline" if world == 1 else "sharded")
     common = {"n_gpus": world, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "f32",
               "data": "synthetic"}
@@ -835,6 +867,14 @@ def main():
             line["uniform"] = {"what": "the same kernel on uniform-random 1M x 128 (north_star's wording): no neighbourhood structure, recall@10 stays far "
                                        "below 0.95 at any practical ef", "value": u["value"], "unit": "queries/s", "recall_at_10": u["recall_at_10"],
                                "ef_search": u["ef_search"], "k1_frac": u["roofline"]["frac"]}
+        if world == 1 and a.mode == "auto" and not a.skip_secondary:
+            ba = argparse.Namespace(**{**vars(a), "n": 2_000_000, "dim": 300, "M": 24, "efc": 200, "ef": 100, "data": "sift", "batch": 10_000,
+                                       "build_reps": 1})
+            b = leg_build(ba, local_rank)
+            line["build"] = {"what": "BASELINE configs[2]: GPU Builder::build of 2M x 300 f32 (M=24, ef_construction=200) + batch=10k search on the graph it "
+                                     "built; cpu_baseline = the reference algorithm's threaded build of a prefix on this box's host threads",
+                             **{k_: b[k_] for k_ in ("value", "unit", "seconds", "recall_at_10_of_built_graph", "ef_search", "config", "search",
+                                                     "recall_at_10_subset_gpu_graph", "cpu_baseline") if k_ in b}}
         out = line
     else:  # sharded
         s = leg_sharded(a, rank, local_rank, world)
@@ -847,6 +887,16 @@ def main():
             r = leg_search(ra, rank, local_rank, world, full=False)
             line["replicas"] = {"what": "configs[1] with the 1M index replicated per GPU and the queries sharded (no collective)", "value": r["value"],
                                 "unit": "queries/s", "k1_frac": r["roofline"]["frac"], "recall_at_10": r["recall_at_10"]}
+        if world > 1 and a.mode == "auto" and not a.skip_secondary:
+            # the denominator of the 1 -> N figure: the SAME 8 sub-indexes on ONE GPU, measured by rank 0 in this very run
+            # (world-size-1 communicator; the other ranks wait at the barrier below)
+            if rank == 0:
+                o = leg_sharded(a, 0, local_rank, 1, full=False)
+                line["one_gpu_same_layout"] = {"what": f"the same {N_SUB} sub-indexes x {a.shard_n}, batch {a.shard_batch}, on ONE GPU of this box (rank 0, "
+                                                       "world-size-1 communicator), same run: the 1-GPU point of this strong-scaling curve",
+                                               "value": o["value"], "unit": "queries/s", "ms_per_step": o["ms_per_step"], "recall_at_10": o["recall_at_10"],
+                                               "merged_eq_protocol": o["merged_eq_protocol"], "k1_frac": o["roofline"]["frac"]}
+            barrier(world)
         line.update({"config": sharded_config(a, world), "recall_at_10": s["recall_at_10"], "ef_search": a.ef, "e2e": s.get("e2e"),
                      "gpu_launches": s["gpu_launches"], "roofline": s["roofline"], "merged_eq_protocol": s["merged_eq_protocol"],
                      "shard0_eq_oracle": s.get("shard0_eq_oracle"), "cpu_baseline": None, "clocks": s["clocks"]})

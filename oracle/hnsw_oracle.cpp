@@ -18,7 +18,9 @@
 //   * rand "0.10" SmallRng::seed_from_u64 + random_range (core:214,257-260): restated here from the
 //     published algorithms (xoshiro256++ seeded by SplitMix64; widening-multiply range sampling with one
 //     bias-reduction step, as in rand 0.9's UniformInt::sample_single_inclusive).  No reference test
-//     pins the stream (seeds come from ThreadRng, tests/all.rs:17,56).
+//     pins the stream (seeds come from ThreadRng, tests/all.rs:17,56).  The generator core and its seeding ARE
+//     pinned to the published known-answer vectors of xoshiro256++ (reference C implementation, state {1,2,3,4})
+//     and of Xoshiro256PlusPlus::seed_from_u64(0) (orc_rng_kat); the range reduction remains unpinned.
 //   * ordered-float "5.0" total order (types:231): NaN greatest and equal to itself, -0 == +0.
 //   * rayon scheduling (core:316-318): threaded build order is nondeterministic by design.
 //
@@ -690,6 +692,15 @@ ORC_API uint32_t orc_layer_schedule(uint64_t n, uint32_t M, float ml, uint64_t* 
 }
 
 // out_ids[orig] = PointId (core:262-270)
+// Known-answer access to the rand restatement: the first `count` next_u64 outputs from a raw state (`state` != null: the xoshiro256++
+// reference implementation's own vector, s = {1,2,3,4}) or from seed_from_u64(seed) (SplitMix64 expansion).  Checked against the
+// published vectors in tests/test_oracle_reference_pins.py.
+ORC_API void orc_rng_kat(const uint64_t* state, uint64_t seed, uint64_t* out, uint32_t count) {
+    Xoshiro256pp rng(seed);
+    if (state) std::memcpy(rng.s, state, sizeof rng.s);
+    for (uint32_t i = 0; i < count; ++i) out[i] = rng.next_u64();
+}
+
 ORC_API void orc_shuffle(uint64_t n, uint64_t seed, uint32_t* out_ids) {
     std::vector<uint32_t> order;
     shuffle_ids(n, seed, order, out_ids);

@@ -58,6 +58,8 @@ def lib():
     L.orc_layer_schedule.restype = C.c_uint32
     L.orc_layer_schedule.argtypes = [C.c_uint64, C.c_uint32, C.c_float, u64p, C.c_uint32]
     L.orc_shuffle.argtypes = [C.c_uint64, C.c_uint64, u32p]
+    L.orc_rng_kat.argtypes = [u64p, C.c_uint64, u64p, C.c_uint32]
+    L.orc_rng_kat.restype = None
     L.orc_build.restype = C.c_void_p
     L.orc_build.argtypes = [f32p, C.c_uint64, C.c_uint32, C.POINTER(Params), u32p]
     L.orc_from_graph.restype = C.c_void_p
@@ -126,6 +128,14 @@ def layer_schedule(n, M=32, ml=None):
 def shuffle(n, seed):
     out = np.empty(n, dtype=np.uint32)
     lib().orc_shuffle(n, seed, _p(out, C.c_uint32))
+    return out
+
+
+def rng_kat(count=10, state=None, seed=0):
+    """First `count` u64 outputs of the rand restatement, from a raw xoshiro256++ state or from seed_from_u64(seed)."""
+    out = np.empty(count, dtype=np.uint64)
+    st = None if state is None else np.ascontiguousarray(state, dtype=np.uint64)
+    lib().orc_rng_kat(None if st is None else _p(st, C.c_uint64), seed, _p(out, C.c_uint64), count)
     return out
 
 

@@ -80,6 +80,19 @@ def test_shuffle_is_a_seeded_permutation(oracle):
     assert (a != oracle.shuffle(1000, 43)).any()
 
 
+def test_rng_core_matches_published_vectors(oracle):
+    """The PointId permutation comes from rand's SmallRng (core:214, 257-260) = xoshiro256++ seeded through SplitMix64 on 64-bit
+    targets; the rand crate is not under /root/reference, so the generator is pinned to the PUBLISHED known-answer vectors:
+    the xoshiro256++ reference implementation's outputs from state {1,2,3,4} (also rand's own `reference` test) and the outputs of
+    Xoshiro256PlusPlus::seed_from_u64(0) (rand's seeding test).  (The range reduction of random_range stays unpinned.)"""
+    ref = [41943041, 58720359, 3588806011781223, 3591011842654386, 9228616714210784205, 9973669472204895162, 14011001112246962877,
+           12406186145184390807, 15849039046786891736, 10450023813501588000]
+    assert oracle.rng_kat(10, state=[1, 2, 3, 4]).tolist() == ref
+    seeded = [5987356902031041503, 7051070477665621255, 6633766593972829180, 211316841551650330, 9136120204379184874, 379361710973160858,
+              15813423377499357806, 15596884590815070553, 5439680534584881407, 1369371744833522710]
+    assert oracle.rng_kat(10, seed=0).tolist() == seeded
+
+
 def test_empty_index(oracle):
     ix, ids = oracle.build(np.zeros((0, 8), dtype=np.float32))
     got, dist, lens = ix.search(np.zeros(8, dtype=np.float32), k=4)
