@@ -358,44 +358,54 @@ def leg_search(a, rank, local_rank, world, full=True):
     nq = a.batch
     host_q = [gen(nq, a.dim, 5000 + 977 * rank + s) for s in range(total)]
     dq = [torch.from_numpy(q).cuda() for q in host_q]
-    lanes = 2
-    d_ids = [torch.empty((nq, K), dtype=torch.int32, device="cuda") for _ in range(lanes)]
-    d_dist = [torch.empty((nq, K), dtype=torch.float32, device="cuda") for _ in range(lanes)]
-    d_len = [torch.empty((nq,), dtype=torch.int32, device="cuda") for _ in range(lanes)]
-    streams = [torch.cuda.ExternalStream(ix.lane_stream(l), device=local_rank) for l in range(lanes)]
+    max_lanes = 4
+    d_ids = [torch.empty((nq, K), dtype=torch.int32, device="cuda") for _ in range(max_lanes)]
+    d_dist = [torch.empty((nq, K), dtype=torch.float32, device="cuda") for _ in range(max_lanes)]
+    d_len = [torch.empty((nq,), dtype=torch.int32, device="cuda") for _ in range(max_lanes)]
+    streams = [torch.cuda.ExternalStream(ix.lane_stream(l), device=local_rank) for l in range(max_lanes)]
     torch.cuda.synchronize()
 
     def step(s, lane):
         ix.search_device(dq[s].data_ptr(), nq, ef, K, d_ids[lane].data_ptr(), d_dist[lane].data_ptr(), d_len[lane].data_ptr(), lane=lane)
 
-    for s in range(a.warmup):
-        step(s, s % lanes)
-    ix.sync()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
-    barrier(world)
-    torch.cuda.synchronize()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(lanes)]
-    t_wall0 = time.time()
-    ev0.record(streams[0])
-    streams[1].wait_event(ev0)
-    launches = 0
-    for s in range(a.warmup, total):
-        step(s, s % lanes)
-        launches += 2  # K1 search_kernel + its (normally idle) overflow-retry launch; the control-block memset is not a kernel
-    for l in range(lanes):
-        ends[l].record(streams[l])
-    for l in range(lanes):
-        ends[l].synchronize()
-    torch.cuda.synchronize()
-    t_wall1 = time.time()
-    barrier(world)
-    dev_ms = reduce_max(max(ev0.elapsed_time(e) for e in ends), world)
-    clocks = sampler.summarize(sampler.window(t_wall0, t_wall1))
-    sampler.stop()
+    def device_arm(lanes):
+        """W warm steps, then exactly K timed steps issued round-robin over `lanes` submission lanes; device time, max over ranks."""
+        for s in range(a.warmup):
+            step(s, s % lanes)
+        ix.sync()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        time.sleep(0.3)
+        barrier(world)
+        torch.cuda.synchronize()
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(lanes)]
+        t_wall0 = time.time()
+        ev0.record(streams[0])
+        for l in range(1, lanes):
+            streams[l].wait_event(ev0)
+        n_launch = 0
+        for s in range(a.warmup, total):
+            step(s, s % lanes)
+            n_launch += 2  # K1 search_kernel + its (normally idle) overflow-retry launch; the control-block memset is not a kernel
+        for l in range(lanes):
+            ends[l].record(streams[l])
+        for l in range(lanes):
+            ends[l].synchronize()
+        torch.cuda.synchronize()
+        t_wall1 = time.time()
+        barrier(world)
+        ms = reduce_max(max(ev0.elapsed_time(e) for e in ends), world)
+        ck = sampler.summarize(sampler.window(t_wall0, t_wall1))
+        sampler.stop()
+        return ms, ck, n_launch
+
+    lanes = a.lanes
+    dev_ms, clocks, launches = device_arm(lanes)
     qps = world * nq * a.steps / (dev_ms / 1e3)
+    sweep = None
+    if a.sweep and full:
+        sweep = {"lanes_ms_per_step": {str(l): device_arm(l)[0] / a.steps for l in (1, 2, 3, 4)}}
 
     # isolated launches (one lane, event-bracketed per launch, back to back), then the algorithmic bytes of the same batches
     iso_ms, alg_bytes = [], []
@@ -416,7 +426,7 @@ def leg_search(a, rank, local_rank, world, full=True):
         "retried_per_launch": retried,
         "roofline": {"bound": "hbm", "achieved": alg / (k_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg / (k_ms / 1e3) / 1e9 / peak, "traffic": None, "kernel": "search_kernel (K1 search_layer)",
-                     "kernel_ms": k_ms, "kernel_ms_note": "timed region / launches, two launches in flight (successive launches overlap at the batch boundary)",
+                     "kernel_ms": k_ms, "kernel_ms_note": f"timed region / launches, {lanes} launches in flight (successive launches overlap at the batch boundary)",
                      "kernel_ms_isolated": float(np.mean(iso_ms)), "frac_isolated": alg / (float(np.mean(iso_ms)) / 1e3) / 1e9 / peak,
                      "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
     }
@@ -433,17 +443,17 @@ def leg_search(a, rank, local_rank, world, full=True):
         h = pinned(nq * a.dim * 4, np.float32, (nq, a.dim))
         h[...] = host_q[s_]
         hqs.append(h)
-    callers = 2
-    hid = [pinned(nq * K * 4, np.uint32, (nq, K)) for _ in range(callers)]
-    hds = [pinned(nq * K * 4, np.float32, (nq, K)) for _ in range(callers)]
-    hln = [pinned(nq * 4, np.uint32, (nq,)) for _ in range(callers)]
+    max_callers = 4
+    hid = [pinned(nq * K * 4, np.uint32, (nq, K)) for _ in range(max_callers)]
+    hds = [pinned(nq * K * 4, np.float32, (nq, K)) for _ in range(max_callers)]
+    hln = [pinned(nq * 4, np.uint32, (nq,)) for _ in range(max_callers)]
     last_ids = {}
 
     def e2e_step(s, t):
         _abi.check(L.idb_search_batch_f32(ix._h, _abi.ptr(hqs[s], C.c_float), nq, ef, K, _abi.ptr(hid[t], C.c_uint32),
                                           _abi.ptr(hds[t], C.c_float), _abi.ptr(hln[t], C.c_uint32)))
 
-    def e2e_run(lo, hi):
+    def e2e_run(lo, hi, callers):
         def work(t):
             for s in range(lo + t, hi, callers):
                 e2e_step(s, t)
@@ -453,13 +463,22 @@ def leg_search(a, rank, local_rank, world, full=True):
         [x.start() for x in th]
         [x.join() for x in th]
 
-    e2e_run(0, a.warmup)
-    barrier(world)
-    t0 = time.perf_counter()
-    e2e_run(a.warmup, total)
-    e2e_s = reduce_max(time.perf_counter() - t0, world)
+    def e2e_arm(callers):
+        e2e_run(0, a.warmup, callers)
+        barrier(world)
+        t0 = time.perf_counter()
+        e2e_run(a.warmup, total, callers)
+        return reduce_max(time.perf_counter() - t0, world)
+
+    callers = a.callers
+    if sweep is not None:
+        sweep["e2e_callers_qps"] = {str(c): world * nq * a.steps / e2e_arm(c) for c in (1, 2, 3, 4) if c != callers}
+    e2e_s = e2e_arm(callers)  # (last: the parity leg below compares the final batch's results)
     res["e2e"] = {"value": world * nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * a.dim * 4,
                   "d2h_bytes_per_step": nq * K * 8 + nq * 4, "callers": callers}
+    if sweep is not None:
+        sweep["e2e_callers_qps"][str(callers)] = res["e2e"]["value"]
+        res["sweep"] = sweep
 
     # ---- CPU baseline (rank 0, N=1 leg only) + parity against it: ids, distances, lengths AND traversal counters -------------
     res["cpu_baseline"] = None
@@ -817,6 +836,9 @@ def main():
     ap.add_argument("--shard-batch", type=int, default=100_000)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-secondary", action="store_true", help="N=1: headline only (no sharded / uniform legs)")
+    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2, 3, 4], help="submission lanes the device-resident arm alternates over")
+    ap.add_argument("--callers", type=int, default=2, choices=[1, 2, 3, 4], help="host threads calling idb_search_batch_f32 in the e2e arm")
+    ap.add_argument("--sweep", action="store_true", help="also time 1..4 lanes / callers (reported under `sweep`)")
     ap.add_argument("--build-reps", type=int, default=2)
     ap.add_argument("--build-cpu-sample", type=int, default=100_000)
     a = ap.parse_args()
@@ -849,28 +871,37 @@ def main():
         res = leg_build(a, local_rank)
         out = {**res, **common, "scaling": "weak"}
     elif mode == "headline":
+        t_leg = time.time()
         h = leg_search(a, rank, local_rank, world)
+        log(f"headline leg took {time.time() - t_leg:.1f}s")
         line = {"metric": "batched QPS at recall@10>=0.95 (1M x 128 f32)", "value": h["value"], "unit": "queries/s", **common,
                 "ms_per_step": h["ms_per_step"], "scaling": "weak"}
         if world == 1 and a.mode == "auto" and not a.skip_secondary:
+            t_leg = time.time()
             s = leg_sharded(a, rank, local_rank, world, full=False)
+            log(f"sharded-layout leg took {time.time() - t_leg:.1f}s")
             line["sharded"] = {"what": f"BASELINE configs[4] on ONE GPU ({N_SUB} sub-indexes x {a.shard_n}, batch {a.shard_batch}): the 1-GPU point of the "
                                        f"strong-scaling curve `--gpus N` reports", "value": s["value"], "unit": "queries/s", "ms_per_step": s["ms_per_step"],
                                "recall_at_10": s["recall_at_10"], "merged_eq_protocol": s["merged_eq_protocol"], "gpu_launches": s["gpu_launches"],
                                "k1_frac": s["roofline"]["frac"]}
         line.update({"config": search_config(a, world, mode), "recall_at_10": h["recall_at_10"], "ef_search": h["ef_search"], "e2e": h.get("e2e"),
                      "gpu_launches": h["gpu_launches"], "retried_per_launch": h["retried_per_launch"], "roofline": h["roofline"],
+                     **({"sweep": h["sweep"]} if "sweep" in h else {}),
                      "cpu_baseline": h.get("cpu_baseline"), "clocks": h["clocks"]})
         if world == 1 and a.mode == "auto" and not a.skip_secondary:
             ua = argparse.Namespace(**{**vars(a), "data": "uniform", "steps": min(a.steps, 10)})
+            t_leg = time.time()
             u = leg_search(ua, rank, local_rank, world, full=False)
+            log(f"uniform-data leg took {time.time() - t_leg:.1f}s")
             line["uniform"] = {"what": "the same kernel on uniform-random 1M x 128 (north_star's wording): no neighbourhood structure, recall@10 stays far "
                                        "below 0.95 at any practical ef", "value": u["value"], "unit": "queries/s", "recall_at_10": u["recall_at_10"],
                                "ef_search": u["ef_search"], "k1_frac": u["roofline"]["frac"]}
         if world == 1 and a.mode == "auto" and not a.skip_secondary:
             ba = argparse.Namespace(**{**vars(a), "n": 2_000_000, "dim": 300, "M": 24, "efc": 200, "ef": 100, "data": "sift", "batch": 10_000,
                                        "build_reps": 1})
+            t_leg = time.time()
             b = leg_build(ba, local_rank)
+            log(f"configs[2] build leg took {time.time() - t_leg:.1f}s")
             line["build"] = {"what": "BASELINE configs[2]: GPU Builder::build of 2M x 300 f32 (M=24, ef_construction=200) + batch=10k search on the graph it "
                                      "built; cpu_baseline = the reference algorithm's threaded build of a prefix on this box's host threads",
                              **{k_: b[k_] for k_ in ("value", "unit", "seconds", "recall_at_10_of_built_graph", "ef_search", "config", "search",
