@@ -193,13 +193,20 @@ def build_graph_with_tool(pts, M, efc, ef, seed, device):
                 os.remove(os.path.join(cache_dir(), f))
 
 
-def obtain_graph(pts, n, dim, data, data_seed, M, efc, ef, seed, device, use_abi, no_cache=False):
+def obtain_graph(pts, n, dim, data, data_seed, M, efc, ef, seed, device, use_abi, no_cache=False, by="gpu"):
     """(points in PointId order, zero, upper, ids).  The graph is the GPU Builder::build's (deterministic in the seed): built
-    in-process when the caller is the CUDA arm (use_abi), else by the C++ tool; cached under gpurun_cache/ (git-ignored)."""
+    in-process when the caller is the CUDA arm (use_abi), else by the C++ tool; cached under gpurun_cache/ (git-ignored).
+    by="oracle" (--graph oracle): the reference algorithm's own threaded CPU build (lib.rs:313-318) instead — BASELINE configs[1]'s
+    "reference-built graph" to the letter; minutes of host time at 1M points, so it is not the default."""
     cp = graph_cache_path(n, dim, data, data_seed, M, efc, seed)
+    if by == "oracle":
+        cp = cp.replace("graph_", "graph_oracle_")
+        use_abi = False
     if os.path.exists(cp) and not no_cache:
         z = np.load(cp)
         log(f"graph loaded from cache {os.path.basename(cp)}")
+        if by == "oracle":
+            GRAPH_HOW["by"] = "oracle (reference algorithm, threaded CPU build, lib.rs:313-318), searched by both arms"
         return permute_points(pts, z["ids"]), z["zero"], [z[f"u{i}"] for i in range(int(z["n_upper"]))], z["ids"]
     t = time.time()
     if use_abi:
@@ -208,6 +215,8 @@ def obtain_graph(pts, n, dim, data, data_seed, M, efc, ef, seed, device, use_abi
         ix, ids = _abi.Index.build(pts, M=M, ef_construction=efc, ef_search=ef, seed=seed, device=device)
         _, zero, upper = ix.export_graph()
         ix.close()
+    elif by == "oracle":
+        ids = None
     elif os.path.exists(TOOL):
         try:
             ids, zero, upper, _ = build_graph_with_tool(pts, M, efc, ef, seed, device)
@@ -222,7 +231,10 @@ def obtain_graph(pts, n, dim, data, data_seed, M, efc, ef, seed, device, use_abi
         ix, ids = O.build(pts, M=M, ef_construction=efc, ef_search=ef, seed=seed, threads=host_threads())
         g = ix.export()
         zero, upper = g.zero, g.upper
-        GRAPH_HOW["by"] = "oracle (reference algorithm, threaded CPU build): no GPU was available to this arm"
+        if by == "oracle":
+            GRAPH_HOW["by"] = "oracle (reference algorithm, threaded CPU build, lib.rs:313-318), searched by both arms"
+        else:
+            GRAPH_HOW["by"] = GRAPH_HOW["sharded"] = "oracle (reference algorithm, threaded CPU build): no GPU was available to this arm"
         log("graph built by the oracle (CPU) — NOT the GPU build's graph")
     log(f"graph built in {time.time() - t:.1f}s (setup, untimed)")
     if not no_cache:
@@ -234,7 +246,7 @@ def obtain_graph(pts, n, dim, data, data_seed, M, efc, ef, seed, device, use_abi
 
 
 GRAPH_NOTE = "GPU Builder::build of this library (deterministic in the seed; untimed setup), searched by both arms"
-GRAPH_HOW = {"by": GRAPH_NOTE}  # replaced when a graph had to be built by the oracle on the CPU (no GPU on the box)
+GRAPH_HOW = {"by": GRAPH_NOTE, "sharded": GRAPH_NOTE}  # replaced when a graph had to be built by the oracle on the CPU (no GPU on the box)
 
 
 def search_config(a, world, mode):
@@ -247,7 +259,7 @@ def search_config(a, world, mode):
 def sharded_config(a, world):
     return {"workload": f"{N_SUB} x {a.shard_n} = {N_SUB * a.shard_n} x {a.dim} f32 sift-shaped synthetic in {N_SUB} sub-indexes by contiguous "
                         f"input range, M={a.M}, ef_construction={a.efc}, ef_search={a.ef}, batch={a.shard_batch} queries/step, k={K}",
-            "graph": GRAPH_HOW["by"], "l2": "every sub-index >> 126 MB L2 and a fresh query batch per step (no flush needed)",
+            "graph": GRAPH_HOW["sharded"], "l2": "every sub-index >> 126 MB L2 and a fresh query batch per step (no flush needed)",
             "parallelism": f"{N_SUB} sub-indexes over {world} GPU(s) ({N_SUB // world} per GPU), per-rank pre-merge + ONE ncclAllGather + merge"}
 
 
@@ -330,7 +342,7 @@ def leg_search(a, rank, local_rank, world, full=True):
     gen = generator(a.data)
     pts = gen(a.n, a.dim, 1)
     p, zero, upper, _ = obtain_graph(pts, a.n, a.dim, a.data, 1, a.M, a.efc, a.ef, a.seed, local_rank, use_abi=True,
-                                     no_cache=a.no_cache or world > 1)
+                                     no_cache=a.no_cache or world > 1, by=a.graph)
     del pts
     ix = _abi.Index.from_graph(p, zero, upper, a.M, a.ef, device=local_rank)
     ix.set_profiling(True)
@@ -767,7 +779,7 @@ def run_reference(a, rank, world):
     if world == 1 or a.mode == "headline":
         gen = generator(a.data)
         pts = gen(a.n, a.dim, 1)
-        p, zero, upper, _ = obtain_graph(pts, a.n, a.dim, a.data, 1, a.M, a.efc, a.ef, a.seed, 0, use_abi=False, no_cache=a.no_cache)
+        p, zero, upper, _ = obtain_graph(pts, a.n, a.dim, a.data, 1, a.M, a.efc, a.ef, a.seed, 0, use_abi=False, no_cache=a.no_cache, by=a.graph)
         ix = O.from_graph(O.Graph(p, zero, upper, a.M, a.ef))
         sample = min(a.batch, a.ref_sample)
         batches = [gen(sample, a.dim, 5000 + s)[:sample] for s in range(a.warmup + a.steps)]
@@ -829,6 +841,9 @@ def main():
     ap.add_argument("--seed", type=int, default=20260923)
     ap.add_argument("--data", default="sift", choices=["sift", "uniform"])
     ap.add_argument("--no-cache", action="store_true")
+    ap.add_argument("--graph", default="gpu", choices=["gpu", "oracle"],
+                    help="headline leg: who builds the graph both arms search — this library's GPU Builder::build (default) or the reference "
+                         "algorithm's threaded CPU build (the oracle; minutes at 1M points)")
     ap.add_argument("--recall-sample", type=int, default=1000)
     ap.add_argument("--ref-sample", type=int, default=10_000)
     ap.add_argument("--ref-sample-sharded", type=int, default=2_000)
@@ -889,7 +904,7 @@ def main():
                      **({"sweep": h["sweep"]} if "sweep" in h else {}),
                      "cpu_baseline": h.get("cpu_baseline"), "clocks": h["clocks"]})
         if world == 1 and a.mode == "auto" and not a.skip_secondary:
-            ua = argparse.Namespace(**{**vars(a), "data": "uniform", "steps": min(a.steps, 10)})
+            ua = argparse.Namespace(**{**vars(a), "data": "uniform", "steps": min(a.steps, 10), "graph": "gpu"})
             t_leg = time.time()
             u = leg_search(ua, rank, local_rank, world, full=False)
             log(f"uniform-data leg took {time.time() - t_leg:.1f}s")
@@ -914,7 +929,7 @@ def main():
                 "strong_scaling_note": "the 1-GPU point of this curve is `sharded.value` of the --gpus 1 line (same 8 sub-indexes on one GPU); that line's "
                                        "primary value is configs[1], as the bench contract requires at N=1"}
         if world > 1 and a.mode == "auto" and not a.skip_secondary:
-            ra = argparse.Namespace(**{**vars(a), "steps": min(a.steps, 10)})
+            ra = argparse.Namespace(**{**vars(a), "steps": min(a.steps, 10), "graph": "gpu"})
             r = leg_search(ra, rank, local_rank, world, full=False)
             line["replicas"] = {"what": "configs[1] with the 1M index replicated per GPU and the queries sharded (no collective)", "value": r["value"],
                                 "unit": "queries/s", "k1_frac": r["roofline"]["frac"], "recall_at_10": r["recall_at_10"]}
