@@ -891,36 +891,52 @@ def main():
         log(f"headline leg took {time.time() - t_leg:.1f}s")
         line = {"metric": "batched QPS at recall@10>=0.95 (1M x 128 f32)", "value": h["value"], "unit": "queries/s", **common,
                 "ms_per_step": h["ms_per_step"], "scaling": "weak"}
-        if world == 1 and a.mode == "auto" and not a.skip_secondary:
+        secondary = world == 1 and a.mode == "auto" and not a.skip_secondary
+
+        def secondary_leg(key, what, fn):
+            """A secondary leg of the N=1 line: its failure is reported under its key and never takes the headline down with it."""
             t_leg = time.time()
+            try:
+                line[key] = {"what": what, **fn()}
+            except Exception as e:  # noqa: BLE001
+                log(f"{key} leg FAILED: {e!r}")
+                line[key] = {"what": what, "error": repr(e)[:300]}
+                try:
+                    torch.cuda.empty_cache()
+                except Exception:  # noqa: BLE001
+                    pass
+            log(f"{key} leg took {time.time() - t_leg:.1f}s")
+
+        def sharded_leg():
             s = leg_sharded(a, rank, local_rank, world, full=False)
-            log(f"sharded-layout leg took {time.time() - t_leg:.1f}s")
-            line["sharded"] = {"what": f"BASELINE configs[4] on ONE GPU ({N_SUB} sub-indexes x {a.shard_n}, batch {a.shard_batch}): the 1-GPU point of the "
-                                       f"strong-scaling curve `--gpus N` reports", "value": s["value"], "unit": "queries/s", "ms_per_step": s["ms_per_step"],
-                               "recall_at_10": s["recall_at_10"], "merged_eq_protocol": s["merged_eq_protocol"], "gpu_launches": s["gpu_launches"],
-                               "k1_frac": s["roofline"]["frac"]}
+            return {"value": s["value"], "unit": "queries/s", "ms_per_step": s["ms_per_step"], "recall_at_10": s["recall_at_10"],
+                    "merged_eq_protocol": s["merged_eq_protocol"], "gpu_launches": s["gpu_launches"], "k1_frac": s["roofline"]["frac"]}
+
+        if secondary:
+            secondary_leg("sharded", f"BASELINE configs[4] on ONE GPU ({N_SUB} sub-indexes x {a.shard_n}, batch {a.shard_batch}): the 1-GPU point of "
+                                     f"the strong-scaling curve `--gpus N` reports", sharded_leg)
         line.update({"config": search_config(a, world, mode), "recall_at_10": h["recall_at_10"], "ef_search": h["ef_search"], "e2e": h.get("e2e"),
                      "gpu_launches": h["gpu_launches"], "retried_per_launch": h["retried_per_launch"], "roofline": h["roofline"],
                      **({"sweep": h["sweep"]} if "sweep" in h else {}),
                      "cpu_baseline": h.get("cpu_baseline"), "clocks": h["clocks"]})
-        if world == 1 and a.mode == "auto" and not a.skip_secondary:
+        def uniform_leg():
             ua = argparse.Namespace(**{**vars(a), "data": "uniform", "steps": min(a.steps, 10), "graph": "gpu"})
-            t_leg = time.time()
             u = leg_search(ua, rank, local_rank, world, full=False)
-            log(f"uniform-data leg took {time.time() - t_leg:.1f}s")
-            line["uniform"] = {"what": "the same kernel on uniform-random 1M x 128 (north_star's wording): no neighbourhood structure, recall@10 stays far "
-                                       "below 0.95 at any practical ef", "value": u["value"], "unit": "queries/s", "recall_at_10": u["recall_at_10"],
-                               "ef_search": u["ef_search"], "k1_frac": u["roofline"]["frac"]}
-        if world == 1 and a.mode == "auto" and not a.skip_secondary:
+            return {"value": u["value"], "unit": "queries/s", "recall_at_10": u["recall_at_10"], "ef_search": u["ef_search"],
+                    "k1_frac": u["roofline"]["frac"]}
+
+        def build_leg():
             ba = argparse.Namespace(**{**vars(a), "n": 2_000_000, "dim": 300, "M": 24, "efc": 200, "ef": 100, "data": "sift", "batch": 10_000,
                                        "build_reps": 1})
-            t_leg = time.time()
             b = leg_build(ba, local_rank)
-            log(f"configs[2] build leg took {time.time() - t_leg:.1f}s")
-            line["build"] = {"what": "BASELINE configs[2]: GPU Builder::build of 2M x 300 f32 (M=24, ef_construction=200) + batch=10k search on the graph it "
-                                     "built; cpu_baseline = the reference algorithm's threaded build of a prefix on this box's host threads",
-                             **{k_: b[k_] for k_ in ("value", "unit", "seconds", "recall_at_10_of_built_graph", "ef_search", "config", "search",
-                                                     "recall_at_10_subset_gpu_graph", "cpu_baseline") if k_ in b}}
+            return {k_: b[k_] for k_ in ("value", "unit", "seconds", "recall_at_10_of_built_graph", "ef_search", "config", "search",
+                                         "recall_at_10_subset_gpu_graph", "cpu_baseline") if k_ in b}
+
+        if secondary:
+            secondary_leg("uniform", "the same kernel on uniform-random 1M x 128 (north_star's wording): no neighbourhood structure, recall@10 stays far "
+                                     "below 0.95 at any practical ef", uniform_leg)
+            secondary_leg("build", "BASELINE configs[2]: GPU Builder::build of 2M x 300 f32 (M=24, ef_construction=200) + batch=10k search on the graph it "
+                                   "built; cpu_baseline = the reference algorithm's threaded build of a prefix on this box's host threads", build_leg)
         out = line
     else:  # sharded
         s = leg_sharded(a, rank, local_rank, world)
