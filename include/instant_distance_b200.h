@@ -103,7 +103,8 @@ IDB_API idb_status idb_index_from_graph_bf16(const float* points, uint64_t n, ui
  * ef_search == 0 uses the index's own ef_search (Hnsw::ef_search, core:195).  out_dist / out_len may be NULL.
  * Thread safety: `Hnsw<P>: Sync` (core:352-356) — any number of host threads may call this on one index at once; each call
  * takes an idle submission lane (own CUDA stream and control state, idb_index_num_lanes() of them) so concurrent callers overlap on
- * the device.
+ * the device.  Buffers may be pageable or pinned (idb_host_alloc); results for pageable output buffers are staged through pinned
+ * memory inside the library, so one caller's read-back never stalls another caller's launches.
  * Device-wide side effect: the per-warp visited tables of the traversal kernels live in a per-device pool shared by every index; the
  * first search/build on a device reserves part of the device's persisting-L2 set-aside for them (cudaLimitPersistingL2CacheSize, as
  * much as the tables in use need, at most the device maximum) and every launch carries an access-policy window for them as a launch

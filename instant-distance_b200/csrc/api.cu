@@ -299,6 +299,46 @@ idb_status DeviceCtx::reserve_l2(size_t bytes) {
     return IDB_OK;
 }
 
+static bool host_ptr_is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+cudaError_t HostOut::enqueue(Lane& ln) {
+    lane = &ln;
+    staged = false;
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) {
+        staged = staged || !host_ptr_is_pinned(parts[i].user);
+        parts[i].off = total;
+        total += (parts[i].bytes + 63) / 64 * 64;
+    }
+    if (staged && total > ln.h_out_cap) {
+        if (ln.h_out) cudaFreeHost(ln.h_out);
+        ln.h_out = nullptr;
+        ln.h_out_cap = 0;
+        const size_t want = total + total / 4;
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&ln.h_out), want, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        ln.h_out_cap = want;
+    }
+    for (int i = 0; i < n; ++i) {
+        void* dst = staged ? static_cast<void*>(ln.h_out + parts[i].off) : parts[i].user;
+        cudaError_t e = cudaMemcpyAsync(dst, parts[i].dev, parts[i].bytes, cudaMemcpyDeviceToHost, ln.stream);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+void HostOut::finish() const {
+    if (!staged) return;
+    for (int i = 0; i < n; ++i) std::memcpy(parts[i].user, lane->h_out + parts[i].off, parts[i].bytes);
+}
+
 void Lane::free_all() {
     cudaFree(ctrl); cudaFree(status); cudaFree(fail_list); cudaFree(counters);
     cudaFree(q); cudaFree(ids); cudaFree(dist); cudaFree(len);
@@ -307,6 +347,7 @@ void Lane::free_all() {
     if (ev1) cudaEventDestroy(ev1);
     if (ev_ctrl) cudaEventDestroy(ev_ctrl);
     if (h_ctrl) cudaFreeHost(h_ctrl);
+    if (h_out) cudaFreeHost(h_out);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -353,7 +394,7 @@ idb_status Index::attach_window(Lane& ln, const LaunchWindow& win) {
 idb_status Index::ensure_lane_scratch(Lane& ln, uint64_t nq) {
     if (!ln.ctrl) {
         CUDA_TRY(cudaMalloc(&ln.ctrl, 64));
-        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&ln.h_ctrl), 64, cudaHostAllocDefault));
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&ln.h_ctrl), 128, cudaHostAllocDefault));  // [0,16): sampled tally, [16,32): host API
         CUDA_TRY(cudaEventCreateWithFlags(&ln.ev_ctrl, cudaEventDisableTiming));
     }
     if (ln.ctrl_pending && cudaEventQuery(ln.ev_ctrl) == cudaSuccess) {  // the previous call's tally has arrived
@@ -828,12 +869,18 @@ idb_status idb_search_batch_f32(idb_index* index, const float* queries, uint64_t
     }
     idb_status st = ix->enqueue_search(ln, ln.q, nq, ef, k, ln.ids, ln.dist, ln.len, nullptr);
     if (st != IDB_OK) return st;
-    CUDA_TRY(cudaMemcpyAsync(out_ids, ln.ids, nq * k * 4, cudaMemcpyDeviceToHost, ln.stream));
-    if (out_dist) CUDA_TRY(cudaMemcpyAsync(out_dist, ln.dist, nq * k * 4, cudaMemcpyDeviceToHost, ln.stream));
-    if (out_len) CUDA_TRY(cudaMemcpyAsync(out_len, ln.len, nq * 4, cudaMemcpyDeviceToHost, ln.stream));
-    uint32_t ctrl[16];
+    HostOut ho;
+    ho.add(out_ids, ln.ids, nq * k * 4);
+    ho.add(out_dist, ln.dist, nq * k * 4);
+    ho.add(out_len, ln.len, nq * 4);
+    CUDA_TRY(ho.enqueue(ln));
+    // The control block comes back through PINNED memory: a device-to-pageable cudaMemcpyAsync blocks inside the driver until the
+    // copy has run (i.e. until this call's K1 has finished) and stalls the launches of other caller threads meanwhile, so concurrent
+    // callers would never have a second batch queued behind the running one.
+    uint32_t* ctrl = ln.h_ctrl + 16;
     CUDA_TRY(cudaMemcpyAsync(ctrl, ln.ctrl, 64, cudaMemcpyDeviceToHost, ln.stream));
     CUDA_TRY(cudaStreamSynchronize(ln.stream));
+    ho.finish();
     ix->note_overflows(ef, nq, ctrl[4], ln.last_b16);
     if (ctrl[12] != 0)  // failures that survived the retry pass
         return fail(IDB_ERR_CAPACITY, "%u of %llu queries overflowed an internal per-query structure (visited table / tie list)",

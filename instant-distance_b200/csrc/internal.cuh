@@ -126,8 +126,10 @@ struct Lane {
     float* q2 = nullptr;          size_t q2_cap = 0;
     uint32_t* ids2 = nullptr;     size_t ids2_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // host API: results land here first when the caller's output buffers are pageable (see HostOut in api.cu)
+    unsigned char* h_out = nullptr; size_t h_out_cap = 0;   // pinned
     // asynchronous read-back of the control block of the lane's last call (how many queries overflowed the b16 tables)
-    uint32_t* h_ctrl = nullptr;      // pinned, 16 words
+    uint32_t* h_ctrl = nullptr;      // pinned, 32 words: [0,16) the sampled overflow tally, [16,32) the host API's read-back
     cudaEvent_t ev_ctrl = nullptr;
     bool ctrl_pending = false;
     int ctrl_b16 = 0;
@@ -139,6 +141,22 @@ struct Lane {
     uint64_t last_nq = 0;
     uint32_t last_launches = 0;
     void free_all();
+};
+
+// Device -> host copy of a batch's results through the lane's stream.  Output buffers in pinned (or registered) host memory receive
+// the copies directly.  Pageable buffers do NOT: a device-to-pageable cudaMemcpyAsync blocks inside the driver until the copy has run
+// (i.e. until this call's K1 has finished) and stalls the launches of other caller threads meanwhile — concurrent callers would never
+// have a second batch queued behind the running one.  Those results are staged in the lane's pinned buffer and copied out after the
+// stream has been synchronised.
+struct HostOut {
+    struct Part { void* user; const void* dev; size_t bytes; size_t off; };
+    Part parts[3];
+    int n = 0;
+    bool staged = false;
+    Lane* lane = nullptr;
+    void add(void* user, const void* dev, size_t bytes) { if (user && bytes) parts[n++] = Part{user, dev, bytes, 0}; }
+    cudaError_t enqueue(Lane& ln);   // after the kernels of the call
+    void finish() const;             // after cudaStreamSynchronize
 };
 
 struct Index {

@@ -305,10 +305,13 @@ idb_status idb_sharded_search_batch_f32_multi(idb_index* const* shards, uint32_t
     st = sharded_search_locked(reinterpret_cast<Index* const*>(shards), n_shards, reinterpret_cast<Comm*>(comm), ln.q2, nq, ef_search, k,
                                ln.ids2, ln.dist, ln.len);
     if (st != IDB_OK) return st;
-    CUDA_TRY(cudaMemcpyAsync(out_ids, ln.ids2, nq * k * 4, cudaMemcpyDeviceToHost, ln.stream));
-    if (out_dist) CUDA_TRY(cudaMemcpyAsync(out_dist, ln.dist, nq * k * 4, cudaMemcpyDeviceToHost, ln.stream));
-    if (out_len) CUDA_TRY(cudaMemcpyAsync(out_len, ln.len, nq * 4, cudaMemcpyDeviceToHost, ln.stream));
+    HostOut ho;  // (pageable output buffers are staged through pinned memory: internal.cuh)
+    ho.add(out_ids, ln.ids2, nq * k * 4);
+    ho.add(out_dist, ln.dist, nq * k * 4);
+    ho.add(out_len, ln.len, nq * 4);
+    CUDA_TRY(ho.enqueue(ln));
     CUDA_TRY(cudaStreamSynchronize(ln.stream));  // every shard's stream was joined into this one
+    ho.finish();
     uint32_t failed = 0;
     for (uint32_t i = 0; i < n_shards; ++i) {
         Lane& sl = reinterpret_cast<Index*>(shards[i])->lanes[0];
