@@ -10,7 +10,7 @@ A "step" = one pass of the hot path (Hnsw::search, lib.rs:352-383) over one batc
 --gpus 1 (auto): BASELINE.json configs[1] — 1M x 128 f32 "SIFT-shaped" synthetic points, M=32, ef_construction=100, ef_search=100
   (raised only if recall@10 < 0.95), batch = 10k queries.  `value` = queries/s with queries + outputs resident in HBM (batches
   issued alternately on two submission lanes, so consecutive launches overlap at the batch boundary); `e2e` = the same through
-  idb_search_batch_f32 with pinned HOST buffers (H2D + D2H inside the timed region, two caller threads).  The line also carries
+  idb_search_batch_f32 with pinned HOST buffers (H2D + D2H inside the timed region, three caller threads).  The line also carries
   `sharded` (BASELINE configs[4] on ONE GPU: 10M x 128 in 8 sub-indexes by contiguous input range, batch 100k — the denominator of
   the 1 -> 8 GPU figure north_star asks for), `uniform` (the same headline kernel on uniform-random data) and `build` (BASELINE
   configs[2]: GPU Builder::build of 2M x 300, M=24, ef_construction=200, then batch=10k search on that graph, next to the threaded CPU
@@ -852,7 +852,7 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-secondary", action="store_true", help="N=1: headline only (no sharded / uniform legs)")
     ap.add_argument("--lanes", type=int, default=2, choices=[1, 2, 3, 4], help="submission lanes the device-resident arm alternates over")
-    ap.add_argument("--callers", type=int, default=2, choices=[1, 2, 3, 4], help="host threads calling idb_search_batch_f32 in the e2e arm")
+    ap.add_argument("--callers", type=int, default=3, choices=[1, 2, 3, 4], help="host threads calling idb_search_batch_f32 in the e2e arm")
     ap.add_argument("--sweep", action="store_true", help="also time 1..4 lanes / callers (reported under `sweep`)")
     ap.add_argument("--build-reps", type=int, default=2)
     ap.add_argument("--build-cpu-sample", type=int, default=100_000)
