@@ -919,6 +919,7 @@ def main():
                      "gpu_launches": h["gpu_launches"], "retried_per_launch": h["retried_per_launch"], "roofline": h["roofline"],
                      **({"sweep": h["sweep"]} if "sweep" in h else {}),
                      "cpu_baseline": h.get("cpu_baseline"), "clocks": h["clocks"]})
+
         def uniform_leg():
             ua = argparse.Namespace(**{**vars(a), "data": "uniform", "steps": min(a.steps, 10), "graph": "gpu"})
             u = leg_search(ua, rank, local_rank, world, full=False)
@@ -953,11 +954,16 @@ def main():
             # the denominator of the 1 -> N figure: the SAME 8 sub-indexes on ONE GPU, measured by rank 0 in this very run
             # (world-size-1 communicator; the other ranks wait at the barrier below)
             if rank == 0:
-                o = leg_sharded(a, 0, local_rank, 1, full=False)
-                line["one_gpu_same_layout"] = {"what": f"the same {N_SUB} sub-indexes x {a.shard_n}, batch {a.shard_batch}, on ONE GPU of this box (rank 0, "
-                                                       "world-size-1 communicator), same run: the 1-GPU point of this strong-scaling curve",
-                                               "value": o["value"], "unit": "queries/s", "ms_per_step": o["ms_per_step"], "recall_at_10": o["recall_at_10"],
-                                               "merged_eq_protocol": o["merged_eq_protocol"], "k1_frac": o["roofline"]["frac"]}
+                what = (f"the same {N_SUB} sub-indexes x {a.shard_n}, batch {a.shard_batch}, on ONE GPU of this box (rank 0, world-size-1 "
+                        "communicator), same run: the 1-GPU point of this strong-scaling curve")
+                try:
+                    o = leg_sharded(a, 0, local_rank, 1, full=False)
+                    line["one_gpu_same_layout"] = {"what": what, "value": o["value"], "unit": "queries/s", "ms_per_step": o["ms_per_step"],
+                                                   "recall_at_10": o["recall_at_10"], "merged_eq_protocol": o["merged_eq_protocol"],
+                                                   "k1_frac": o["roofline"]["frac"]}
+                except Exception as e:  # noqa: BLE001  (the other ranks are waiting at the barrier: never leave them there)
+                    log(f"one_gpu_same_layout leg FAILED: {e!r}")
+                    line["one_gpu_same_layout"] = {"what": what, "error": repr(e)[:300]}
             barrier(world)
         line.update({"config": sharded_config(a, world), "recall_at_10": s["recall_at_10"], "ef_search": a.ef, "e2e": s.get("e2e"),
                      "gpu_launches": s["gpu_launches"], "roofline": s["roofline"], "merged_eq_protocol": s["merged_eq_protocol"],
