@@ -84,3 +84,25 @@ def test_params_struct_field_order_and_widths():
         r_fields.append((name.strip(), kind))
     assert [k for _, k in r_fields] == [k for _, k in c_fields]
     assert [n.lower() for n, _ in r_fields] == [n.lower() for n, _ in c_fields]
+
+
+def test_shim_source_is_well_formed_and_exposes_the_reference_surface():
+    """No rustc here: at least the delimiters balance and every public item of the reference's surface (SURVEY §8b:
+    Builder / Hnsw / HnswMap / Search / Point / PointId / Item / MapItem / Heuristic) is defined."""
+    src = open(RUST).read()
+    text = re.sub(r"//.*", "", src)
+    text = re.sub(r'"(\\.|[^"\\])*"', '""', text)
+    text = re.sub(r"'(\\.|[^'\\])'", "''", text)
+    stack, pairs = [], {")": "(", "]": "[", "}": "{"}
+    for ch in text:
+        if ch in "([{":
+            stack.append(ch)
+        elif ch in ")]}":
+            assert stack and stack.pop() == pairs[ch], "unbalanced delimiters in the Rust shim"
+    assert not stack
+    for item in ("struct Builder", "struct Hnsw", "struct HnswMap", "struct Search", "trait Point", "struct PointId", "struct Item",
+                 "struct MapItem", "struct Heuristic"):
+        assert re.search(r"\bpub " + item + r"\b", src), item
+    for method in ("fn ef_construction", "fn ef_search", "fn select_heuristic", "fn ml", "fn seed", "fn build_hnsw", "fn build<", "fn search<",
+                   "fn iter", "fn builder"):
+        assert "pub " + method in src, method
