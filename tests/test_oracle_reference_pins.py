@@ -175,3 +175,31 @@ def test_ties_grid_data_search_is_well_defined(oracle):
             assert L <= ef and len(set(ids[i][:L].tolist())) == L
             keys = list(zip(dist[i][:L].tolist(), ids[i][:L].tolist()))
             assert keys == sorted(keys)
+
+
+def test_nan_distances_follow_ordered_float_semantics(oracle):
+    """`Candidate` orders by OrderedFloat<f32> distance, then pid (types.rs:228-234).  ordered-float's documented total order — NaN is
+    greater than every other value and equal to itself — is not under /root/reference, so the oracle's rendering of it is stated
+    here: a query with a NaN coordinate makes every distance NaN, all keys then tie on distance, and the result is what the
+    traversal reaches, ordered by PointId alone; a point row with a NaN sorts after every finite distance."""
+    pts = datagen.uniform(300, 8, 1)
+    ix, _ = oracle.build(pts, seed=1, threads=1)
+    q = datagen.uniform(1, 8, 2)
+    q[0, 3] = np.nan
+    ids, dist, lens = ix.search(q, ef_search=20, k=20)
+    n = int(lens[0])
+    assert n > 0 and np.isnan(dist[0, :n]).all()
+    assert (np.diff(ids[0, :n].astype(np.int64)) > 0).all()  # ties on distance are broken by ascending pid
+    # one poisoned ROW: it can only ever be the last item of a result
+    pts2 = pts.copy()
+    pts2[17, 0] = np.nan
+    ix2, ids_map = oracle.build(pts2, seed=1, threads=1)
+    q2 = datagen.uniform(50, 8, 3)
+    ids2, dist2, lens2 = ix2.search(q2, ef_search=300, k=300)
+    for r in range(50):
+        m = int(lens2[r])
+        d = dist2[r, :m]
+        finite = d[~np.isnan(d)]
+        assert (np.diff(finite) >= 0).all()
+        if np.isnan(d).any():
+            assert np.isnan(d[-1]) and np.isnan(d).sum() == 1 and ids2[r, m - 1] == ids_map[17]
