@@ -203,11 +203,15 @@ def obtain_graph(pts, n, dim, data, data_seed, M, efc, ef, seed, device, use_abi
         cp = cp.replace("graph_", "graph_oracle_")
         use_abi = False
     if os.path.exists(cp) and not no_cache:
-        z = np.load(cp)
-        log(f"graph loaded from cache {os.path.basename(cp)}")
-        if by == "oracle":
-            GRAPH_HOW["by"] = "oracle (reference algorithm, threaded CPU build, lib.rs:313-318), searched by both arms"
-        return permute_points(pts, z["ids"]), z["zero"], [z[f"u{i}"] for i in range(int(z["n_upper"]))], z["ids"]
+        try:
+            z = np.load(cp)
+            got = permute_points(pts, z["ids"]), z["zero"], [z[f"u{i}"] for i in range(int(z["n_upper"]))], z["ids"]
+            log(f"graph loaded from cache {os.path.basename(cp)}")
+            if by == "oracle":
+                GRAPH_HOW["by"] = "oracle (reference algorithm, threaded CPU build, lib.rs:313-318), searched by both arms"
+            return got
+        except Exception as e:  # noqa: BLE001  (a truncated file from an interrupted run: rebuild)
+            log(f"graph cache {os.path.basename(cp)} unreadable ({e!r}); rebuilding")
     t = time.time()
     if use_abi:
         from instant_distance_b200 import _abi
@@ -239,7 +243,9 @@ def obtain_graph(pts, n, dim, data, data_seed, M, efc, ef, seed, device, use_abi
     log(f"graph built in {time.time() - t:.1f}s (setup, untimed)")
     if not no_cache:
         try:
-            np.savez(cp, ids=ids, zero=zero, n_upper=len(upper), **{f"u{i}": u for i, u in enumerate(upper)})
+            tmp = cp[:-4] + f".{os.getpid()}.tmp.npz"  # written whole, then renamed: a reader never sees a partial file
+            np.savez(tmp, ids=ids, zero=zero, n_upper=len(upper), **{f"u{i}": u for i, u in enumerate(upper)})
+            os.replace(tmp, cp)
         except Exception as e:  # cache is best effort
             log("cache write failed:", e)
     return permute_points(pts, ids), zero, upper, ids
